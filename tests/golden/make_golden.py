@@ -1,0 +1,212 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on CPU.
+
+Run in the authoring container only (`python tests/golden/make_golden.py`); the GPU box has
+no /root/reference.  Every array stored here is an input or an output of a reference call;
+the reference call that produced it is named in the `ref_call` string of each case.
+
+The lookup *index / validity* vectors are produced by replaying, with eager torch fp32 ops,
+exactly the expressions the reference evaluates (methods/raft/model/utils.py:70-71,77 and
+ATen GridSampler.h:30) -- the reference never returns its floor indices, so this is the
+index oracle.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from _refimport import load_reference  # noqa: E402
+
+torch.manual_seed(0)
+torch.set_num_threads(1)
+of, corr_mod, utils, RAFT = load_reference()
+from optical_flow.metrics import AverageEndPointError  # noqa: E402
+from optical_flow.metrics.epe import end_point_error  # noqa: E402
+from optical_flow.operator.operator import warp_grid  # noqa: E402
+
+
+def g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def save(name, **arrays):
+    out = {}
+    for k, v in arrays.items():
+        if isinstance(v, torch.Tensor):
+            v = v.detach().cpu().numpy()
+        out[k] = v
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+# ------------------------------------------------------------------ warp (operator.py:8-56)
+def make_warp():
+    cases = {}
+    idx = 0
+    for (b, c, h, w, sigma) in [(2, 3, 17, 23, 3.0), (1, 1, 9, 40, 12.0), (1, 4, 33, 6, 1.0), (1, 3, 1, 7, 2.0), (1, 2, 5, 1, 2.0)]:
+        frame = torch.rand(b, c, h, w, generator=g(10 + idx))
+        flow_px = sigma * torch.randn(b, 2, h, w, generator=g(20 + idx))
+        flow = of.normalize(flow_px)
+        cases[f"frame{idx}"] = frame
+        cases[f"flow_px{idx}"] = flow_px
+        cases[f"flow{idx}"] = flow
+        cases[f"out{idx}"] = of.warp(frame, flow)
+        cases[f"grid{idx}"] = warp_grid(flow.permute(0, 2, 3, 1))
+        idx += 1
+    cases["n"] = np.int64(idx)
+    # every mode / padding / align_corners combination the kernel implements
+    frame = torch.rand(2, 3, 12, 15, generator=g(31))
+    flow = of.normalize(4.0 * torch.randn(2, 2, 12, 15, generator=g(32)))
+    cases["opt_frame"] = frame
+    cases["opt_flow"] = flow
+    for mode in ("bilinear", "nearest"):
+        for pad in ("zeros", "border", "reflection"):
+            for ac in (False, True):
+                cases[f"opt_{mode}_{pad}_{int(ac)}"] = of.warp(frame, flow, mode=mode, padding_mode=pad, align_corners=ac)
+    save("warp", ref_call="optical_flow.warp(frame, optical_flow.normalize(flow_px)); warp_grid", **cases)
+
+
+# ------------------------------------------- scale / normalize / resize / integrate / upflow8
+def make_resize():
+    cases = {}
+    flow = 10.0 * torch.randn(2, 2, 9, 13, generator=g(40))
+    cases["flow"] = flow
+    cases["scale_2"] = of.scale(flow, 2)
+    cases["scale_3_m1"] = of.scale(flow, (3, -1))
+    cases["normalize"] = of.normalize(flow)
+    cases["denormalize"] = of.denormalize(flow)
+    cases["resize_20_31"] = of.resize(flow, size=(20, 31))
+    cases["resize_4_5"] = of.resize(flow, size=(4, 5))
+    cases["resize_9_13"] = of.resize(flow, size=(9, 13))
+    cases["resize_sf2"] = of.resize(flow, scale_factor=2)
+    cases["resize_sf2p5"] = of.resize(flow, scale_factor=2.5)
+    cases["resize_sf0p5"] = of.resize(flow, scale_factor=0.5)
+    small = 5.0 * torch.randn(2, 2, 6, 11, generator=g(41))
+    cases["small"] = small
+    cases["upflow8"] = utils.upflow8(small)
+    f1 = of.normalize(2.0 * torch.randn(1, 2, 10, 14, generator=g(42)))
+    f2 = of.normalize(2.0 * torch.randn(1, 2, 10, 14, generator=g(43)))
+    f3 = of.normalize(2.0 * torch.randn(1, 2, 10, 14, generator=g(44)))
+    cases["int_f1"], cases["int_f2"], cases["int_f3"] = f1, f2, f3
+    cases["integrate"] = of.integrate(f1, f2, f3)
+    save("resize", ref_call="optical_flow.scale/normalize/denormalize/resize/integrate; model.utils.upflow8", **cases)
+
+
+# -------------------------------------------------- CorrBlock (corr.py:38-87, utils.py:64-86)
+def lookup_index_oracle(coords, pyramid, radius):
+    """floor indices and validity bits of every lookup tap, replayed with eager torch fp32 ops."""
+    b, _, h, w = coords.shape
+    d = 2 * radius + 1
+    c = coords.permute(0, 2, 3, 1).reshape(b * h * w, 2)
+    off = torch.linspace(-radius, radius, d)
+    idx = torch.empty(b * h * w, len(pyramid), 2, d, dtype=torch.int32)
+    valid = torch.empty(b * h * w, len(pyramid), d * d, dtype=torch.uint8)
+    for lvl, p in enumerate(pyramid):
+        H, W = p.shape[-2:]
+        cen = c / 2 ** lvl
+        x = cen[:, 0:1] + off[None]            # (Q, d)  x + dy[i]   (corr.py:66-70)
+        y = cen[:, 1:2] + off[None]            # (Q, d)  y + dx[j]
+        xg = 2 * x / (W - 1) - 1               # utils.py:70
+        yg = 2 * y / (H - 1) - 1               # utils.py:71
+        ix = ((xg + 1) / 2) * (W - 1)          # GridSampler.h:30
+        iy = ((yg + 1) / 2) * (H - 1)
+        idx[:, lvl, 0] = torch.floor(ix).to(torch.int32)
+        idx[:, lvl, 1] = torch.floor(iy).to(torch.int32)
+        m = (xg[:, :, None] > -1) & (yg[:, None, :] > -1) & (xg[:, :, None] < 1) & (yg[:, None, :] < 1)  # utils.py:77
+        valid[:, lvl] = m.reshape(-1, d * d).to(torch.uint8)
+    return idx, valid
+
+
+def make_corr():
+    cases = {}
+    # main case: default CorrBlock (4 levels, radius 4) on a 16x16 feature grid
+    b, c, h, w = 1, 64, 16, 16
+    f1 = torch.randn(b, c, h, w, generator=g(50))
+    f2 = torch.randn(b, c, h, w, generator=g(51))
+    blk = corr_mod.CorrBlock(f1, f2, num_levels=4, radius=4)
+    cases["fmap1"], cases["fmap2"] = f1, f2
+    cases["volume_shape"] = np.array(corr_mod.CorrBlock.corr(f1, f2).shape)
+    for i, p in enumerate(blk.corr_pyramid):
+        cases[f"pyr{i}"] = p
+    grid = utils.coords_grid(b, h, w)
+    cases["coords_grid"] = grid
+    coord_sets = {
+        "int": grid.clone(),                                                  # RAFT iteration 0
+        "noise": grid + 2.5 * torch.randn(b, 2, h, w, generator=g(52)),
+    }
+    for name, co in coord_sets.items():
+        cases[f"coords_{name}"] = co
+        cases[f"lookup_{name}"] = blk(co)
+        idx, valid = lookup_index_oracle(co, blk.corr_pyramid, 4)
+        cases[f"idx_{name}"] = idx
+        cases[f"valid_{name}"] = valid
+    # batch 2, non-square, 3 levels: far-out-of-bounds and half-pixel coordinates
+    b, c, h, w = 2, 32, 8, 14
+    f1 = torch.randn(b, c, h, w, generator=g(150))
+    f2 = torch.randn(b, c, h, w, generator=g(151))
+    blk = corr_mod.CorrBlock(f1, f2, num_levels=3, radius=4)
+    cases["b2_fmap1"], cases["b2_fmap2"] = f1, f2
+    for i, p in enumerate(blk.corr_pyramid):
+        cases[f"b2_pyr{i}"] = p
+    grid = utils.coords_grid(b, h, w)
+    coord_sets = {
+        "far": grid + 15.0 * torch.randn(b, 2, h, w, generator=g(53)),        # many taps out of bounds
+        "half": grid + 0.5,
+    }
+    for name, co in coord_sets.items():
+        cases[f"coords_{name}"] = co
+        cases[f"lookup_{name}"] = blk(co)
+        idx, valid = lookup_index_oracle(co, blk.corr_pyramid, 4)
+        cases[f"idx_{name}"] = idx
+        cases[f"valid_{name}"] = valid
+    # odd sizes: pyramid floor semantics 13x21 -> 6x10 -> 3x5 -> 1x2 ; radius 3, 3 levels
+    f1o = torch.randn(1, 32, 13, 21, generator=g(54))
+    f2o = torch.randn(1, 32, 13, 21, generator=g(55))
+    blk_o = corr_mod.CorrBlock(f1o, f2o, num_levels=3, radius=3)
+    co = utils.coords_grid(1, 13, 21) + 3.0 * torch.randn(1, 2, 13, 21, generator=g(56))
+    cases["odd_fmap1"], cases["odd_fmap2"], cases["odd_coords"] = f1o, f2o, co
+    for i, p in enumerate(blk_o.corr_pyramid):
+        cases[f"odd_pyr{i}"] = p
+    cases["odd_lookup"] = blk_o(co)
+    idx, valid = lookup_index_oracle(co, blk_o.corr_pyramid, 3)
+    cases["odd_idx"], cases["odd_valid"] = idx, valid
+    # bilinear_sampler with mask=True (utils.py:76-78)
+    img = torch.rand(3, 2, 7, 9, generator=g(57))
+    pts = torch.rand(3, 5, 4, 2, generator=g(58)) * torch.tensor([10.0, 8.0]) - 1.0
+    pts[0, 0, 0] = torch.tensor([0.0, 0.0])
+    pts[0, 0, 1] = torch.tensor([8.0, 6.0])
+    pts[0, 0, 2] = torch.tensor([4.0, 3.0])
+    s, m = utils.bilinear_sampler(img, pts, mask=True)
+    cases["bs_img"], cases["bs_pts"], cases["bs_out"], cases["bs_mask"] = img, pts, s, m
+    save("corr", ref_call="model.corr.CorrBlock(f1,f2)(coords); CorrBlock.corr; model.utils.bilinear_sampler/coords_grid", **cases)
+
+
+# ------------------------------------------------------ convex upsample (raft.py:73-85) + EPE
+def make_upsample_epe():
+    cases = {}
+    flow = 2.0 * torch.randn(2, 2, 6, 9, generator=g(60))
+    mask = 3.0 * torch.randn(2, 576, 6, 9, generator=g(61))
+    cases["flow"], cases["mask"] = flow, mask
+    cases["up"] = RAFT.upsample_flow(flow, mask)
+    pred = 3.0 * torch.randn(3, 2, 11, 17, generator=g(62))
+    target = pred + torch.randn(3, 2, 11, 17, generator=g(63))
+    valid = (torch.rand(3, 11, 17, generator=g(64)) > 0.2).float()
+    cases["pred"], cases["target"], cases["valid"] = pred, target, valid
+    cases["epe_map"] = end_point_error(pred, target, reduce=False)
+    cases["epe_mean"] = end_point_error(pred, target)
+    m = AverageEndPointError()
+    m.update(pred, target, valid)
+    cases["m1_sum"], cases["m1_total"], cases["m1_compute"] = m.sum_epe.clone(), m.total.clone(), m.compute()
+    m.update(pred * 0.5, target)
+    cases["m2_sum"], cases["m2_total"], cases["m2_compute"] = m.sum_epe.clone(), m.total.clone(), m.compute()
+    save("upsample_epe", ref_call="RAFT.upsample_flow; optical_flow.metrics.epe.end_point_error / AverageEndPointError", **cases)
+
+
+if __name__ == "__main__":
+    make_warp()
+    make_resize()
+    make_corr()
+    make_upsample_epe()
