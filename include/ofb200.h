@@ -1,0 +1,172 @@
+/*
+ * ofb200.h -- C ABI of libofb200.so: hand-written sm_100a kernels for the data-parallel hot
+ * path of awaelchli/torch-optical-flow (flow warp + validity mask, flow resize / upsampling,
+ * RAFT correlation pyramid + lookup, end-point-error reduction).
+ *
+ * The reference is pure Python and has no FFI layer: its boundary is the Python call
+ * surface (optical_flow.operator, methods/raft/model).  Each entry point below replaces the
+ * ATen op sequence behind one reference function; the Python shims in
+ * torch-optical-flow_b200/{optical_flow,model}/ keep the reference's names, arguments and
+ * error behaviour and call these through ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless a name ends in
+ *     _host; tensors are dense row-major in the layouts stated per function
+ *   - the last argument is the CUDA stream (cudaStream_t passed as void*; NULL = default)
+ *   - returns 0 on success, a negative OFB_E* code for a rejected argument, or a positive
+ *     cudaError_t for a CUDA failure; never throws, never allocates device memory, never
+ *     synchronises (ofb_corr_plan_* are the only calls that touch the driver outside a
+ *     stream: they encode TMA descriptors on the host)
+ *   - there is no CPU compute path: without a CUDA device every call fails
+ */
+#ifndef OFB200_H_
+#define OFB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OFB_VERSION 100
+
+#define OFB_OK 0
+#define OFB_EINVAL (-1)       /* bad size / null pointer / unsupported enum value          */
+#define OFB_EUNSUPPORTED (-2) /* valid request this build has no kernel for              */
+#define OFB_EALIGN (-3)       /* pointer or pitch not aligned as the kernel requires     */
+#define OFB_EDRIVER (-4)      /* driver entry point (cuTensorMapEncodeTiled) unavailable */
+
+#define OFB_MODE_BILINEAR 0
+#define OFB_MODE_NEAREST 1
+#define OFB_PAD_ZEROS 0
+#define OFB_PAD_BORDER 1
+#define OFB_PAD_REFLECTION 2
+
+#define OFB_DTYPE_F32 0
+#define OFB_DTYPE_BF16 1
+
+#define OFB_MAX_LEVELS 4
+
+int ofb_version(void);
+const char* ofb_strerror(int code);
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+int64_t ofb_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * K1  backward warp + validity mask.
+ * Replaces optical_flow.warp (optical_flow/operator/operator.py:8-33) including warp_grid
+ * (operator.py:36-56): grid = (linspace(-1,1,W)[j] + flow_x, linspace(-1,1,H)[i] + flow_y),
+ * out = grid_sample(frame, grid, mode, padding_mode, align_corners).
+ *   frame (B,C,H,W) fp32 NCHW, or (B,H,W,C) when channels_last != 0
+ *   flow  (B,2,H,W) fp32, normalised units (optical_flow.normalize)
+ *   out   (B,C,H,W) fp32 NCHW
+ *   valid_or_null (B,H,W) u8: 1 iff -1 < grid < 1 on both axes -- the predicate of
+ *                 bilinear_sampler's mask (methods/raft/model/utils.py:76-78)
+ *   variant: 0 = auto, 1 = direct gather, 2 = shared-memory staged neighbourhood
+ * ------------------------------------------------------------------------------------- */
+int ofb_warp_f32(const float* frame, const float* flow, float* out, uint8_t* valid_or_null,
+                 int B, int C, int H, int W, int mode, int padding_mode, int align_corners,
+                 int channels_last, int variant, void* stream);
+
+/* warp_grid alone (operator.py:36-56): flow (B,H,W,2) -> grid (B,H,W,2). */
+int ofb_warp_grid_f32(const float* flow_bhw2, float* grid_bhw2, int B, int H, int W, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * scale / normalize / denormalize (operator.py:59-82,117-146): out[b,0] = in[b,0]*fx,
+ * out[b,1] = in[b,1]*fy over (B,2,H,W) fp32.
+ * ------------------------------------------------------------------------------------- */
+int ofb_scale_flow_f32(const float* flow, float* out, int B, int64_t HW, float fx, float fy, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K4a  bilinear resize with per-channel magnitude rescale.
+ * Replaces F.interpolate(bilinear) + scale in optical_flow.resize (operator.py:85-114,
+ * align_corners = 0) and 8 * F.interpolate(align_corners=True) in upflow8
+ * (methods/raft/model/utils.py:89-91).  in (N,C,H,W) -> out (N,C,Ho,Wo); channel c is
+ * multiplied by mul_x when c is even, mul_y when odd.
+ * ------------------------------------------------------------------------------------- */
+int ofb_resize_bilinear_f32(const float* in, float* out, int N, int C, int H, int W, int Ho, int Wo,
+                            int align_corners, float mul_x, float mul_y, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K4b  convex 8x flow upsampling.  Replaces RAFT.upsample_flow
+ * (methods/raft/model/raft.py:73-85): flow (N,2,h,w), mask (N,576,h,w) -> out (N,2,8h,8w).
+ * ------------------------------------------------------------------------------------- */
+int ofb_convex_upsample_f32(const float* flow, const float* mask, float* out, int N, int h, int w, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K4c  end-point-error reduction.  Replaces AverageEndPointError.update
+ * (optical_flow/metrics/epe.py:25-35): acc[0] += sum of sqrt(dx^2+dy^2) over pixels with
+ * valid >= 0.5 (all pixels when valid_or_null is NULL), acc[1] += their count.
+ * pred, target (B,2,H,W) fp32; valid (B,H,W) fp32; acc = double[2] on the device, updated
+ * atomically (zero it before the first call; one ncclAllReduce(sum) of it gives the
+ * dist_reduce_fx="sum" semantics of epe.py:22-23).
+ * ofb_epe_map_f32: end_point_error(reduce=False) (epe.py:41-61) -> out (B,H,W).
+ * ------------------------------------------------------------------------------------- */
+int ofb_epe_reduce_f32(const float* pred, const float* target, const float* valid_or_null,
+                       double* acc, int B, int H, int W, void* stream);
+int ofb_epe_map_f32(const float* pred, const float* target, float* out, int B, int H, int W, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Correlation pyramid layout (owned by the caller, described by ofb_pyramid_layout).
+ * Level l of query q = (b, y, x) is an h_l x w_l image, h_l = floor(h / 2^l):
+ *     element (q, yy, xx) lives at  base[l] + q * q_stride[l] + yy * row_pitch[l] + xx
+ * (strides in ELEMENTS of the pyramid dtype).  ofb_pyramid_layout fills the strides the
+ * tensor-core builder needs (row_pitch multiple of 8 elements, q_stride multiple of 8) and
+ * returns the total element count per level through elems[l] (= B*h*w*q_stride[l]).
+ * ------------------------------------------------------------------------------------- */
+typedef struct ofb_pyramid {
+    void* base[OFB_MAX_LEVELS];
+    int64_t q_stride[OFB_MAX_LEVELS];
+    int32_t row_pitch[OFB_MAX_LEVELS];
+    int32_t lvl_h[OFB_MAX_LEVELS];
+    int32_t lvl_w[OFB_MAX_LEVELS];
+    int32_t levels;
+    int32_t dtype; /* OFB_DTYPE_F32 or OFB_DTYPE_BF16 */
+} ofb_pyramid;
+
+int ofb_pyramid_layout(int h, int w, int levels, int padded, ofb_pyramid* pyr_host, int64_t elems_host[OFB_MAX_LEVELS]);
+
+/* ---------------------------------------------------------------------------------------
+ * K2  all-pairs correlation pyramid.  Replaces CorrBlock.corr + CorrBlock.__init__
+ * (methods/raft/model/corr.py:38-54,79-87): corr[b,p,q] = sum_c f1[b,c,p] f2[b,c,q] / sqrt(C),
+ * levels 1.. = 2x2 average pooling over the target (q) image, complete blocks only.
+ *
+ * Step 1, ofb_corr_prep_bf16: fmap (B,C,h,w) fp32 NCHW -> K-major bf16 operand (B,h*w,C)
+ *         (cast + transpose in one pass; replaces the .view/.transpose of corr.py:82-85).
+ * Step 2, ofb_corr_pyramid_bf16: tcgen05/TMEM GEMM tiles fed by TMA, bf16 x bf16 -> fp32
+ *         accumulate, 1/sqrt(C) scale and all pooled levels produced in the epilogue.
+ *         f1_km, f2_km: (B, h*w, C) bf16 from step 1 (C multiple of 64, <= 256).
+ *         pyr: layout from ofb_pyramid_layout(padded = 1), dtype BF16 or F32.
+ *         cta_group: 0 = auto, 1 = one CTA per tile, 2 = CTA pair (cta_group::2).
+ * ofb_corr_pyramid_simt_f32: plain CUDA-core builder (fp32 in, fp32 out) used by tests as an
+ *         on-device cross-check and for shapes the tensor-core kernel rejects.
+ * ------------------------------------------------------------------------------------- */
+int ofb_corr_prep_bf16(const float* fmap_nchw, void* out_km_bf16, int B, int C, int HW, void* stream);
+int ofb_corr_pyramid_bf16(const void* f1_km, const void* f2_km, const ofb_pyramid* pyr_host,
+                          int B, int C, int h, int w, float scale, int cta_group, void* stream);
+int ofb_corr_pyramid_simt_f32(const float* fmap1, const float* fmap2, const ofb_pyramid* pyr_host,
+                              int B, int C, int h, int w, float scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K3  pyramid lookup.  Replaces CorrBlock.__call__ + bilinear_sampler
+ * (methods/raft/model/corr.py:56-77, methods/raft/model/utils.py:64-80): for every query,
+ * level and window cell (i,j): bilinear sample (zeros outside, align_corners=True after the
+ * reference's normalise/un-normalise round trip) of the query's level slice at
+ * (x/2^l + i - r, y/2^l + j - r); out channel = l*(2r+1)^2 + i*(2r+1) + j.
+ *   coords (B,2,h,w) fp32 (ch0 = x, ch1 = y);  out (B, L*(2r+1)^2, h, w) fp32
+ *   idx_or_null   (B*h*w, L, 2, 2r+1) int32 floor indices (x taps then y taps)
+ *   valid_or_null (B*h*w, L, (2r+1)^2) u8   utils.py:77 predicate per sample
+ * ------------------------------------------------------------------------------------- */
+int ofb_corr_lookup(const ofb_pyramid* pyr_host, const float* coords, float* out,
+                    int32_t* idx_or_null, uint8_t* valid_or_null, int B, int h, int w, int radius,
+                    void* stream);
+
+/* bilinear_sampler (utils.py:64-80) for arbitrary images: img (N,C,H,W), coords (N,Ho,Wo,2)
+ * pixel units -> out (N,C,Ho,Wo) [+ mask (N,Ho,Wo) fp32 0/1]. */
+int ofb_bilinear_sampler_f32(const float* img, const float* coords, float* out, float* mask_or_null,
+                             int N, int C, int H, int W, int Ho, int Wo, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OFB200_H_ */

@@ -1,0 +1,539 @@
+"""GPU parity tests: the CUDA path (through the Python shims -> C ABI -> sm_100a kernels) against
+the CPU oracle on the same seeded inputs, against the committed golden vectors produced by the
+reference itself, and -- at full BASELINE sizes -- through size-independent properties.
+
+Tolerances (BASELINE.md section 5 / north_star):
+  warp, resize, upflow8, convex upsample : max-abs <= 1e-5 * max(1, |ref|_inf)   (fp32)
+  lookup floor indices / validity masks   : bit-exact
+  lookup values (same pyramid)            : max-abs <= 1e-5 * max(1, |ref|_inf)
+  correlation pyramid (bf16 in, fp32 acc, bf16 stored) : rel-Frobenius <= 4e-3 per level and
+                                            max-abs <= 4e-2 * rms vs the fp32 reference
+  EPE sum / count                         : rel <= 1e-6 / exact
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import ofb200
+
+    ofb200.load()     # fail loudly if the extension is missing
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+def maxabs(a, b):
+    return float(np.max(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)))) if np.size(a) else 0.0
+
+
+def tol(ref, eps=1e-5):
+    return eps * max(1.0, float(np.abs(ref).max()))
+
+
+def rng(seed):
+    return np.random.default_rng(seed)
+
+
+# =============================================================================== K1 warp
+def test_warp_reference_known_answers():
+    """reference tests/operator/test_operator.py:6-38, CPU tensors in, exact equality."""
+    from optical_flow import normalize, warp
+
+    img = torch.tensor([[[1.0, 2.0]]]).unsqueeze(0)
+    flow = torch.tensor([[[1.0, 0.0]], [[0.0, 0.0]]]).unsqueeze(0)
+    assert torch.equal(warp(img, normalize(flow)), torch.tensor([[[2.0, 2.0]]]).unsqueeze(0))
+    img = torch.tensor([[[1.0], [2.0]]]).unsqueeze(0)
+    flow = torch.tensor([[[0.0], [0.0]], [[1.0], [0.0]]]).unsqueeze(0)
+    assert torch.equal(warp(img, normalize(flow)), torch.tensor([[[2.0], [2.0]]]).unsqueeze(0))
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_warp_golden(golden, variant):
+    from optical_flow import normalize, warp
+
+    g = golden("warp")
+    for i in range(int(g["n"])):
+        frame, flow_px = T(g[f"frame{i}"]), T(g[f"flow_px{i}"])
+        flow = normalize(flow_px)
+        assert maxabs(N(flow), g[f"flow{i}"]) == 0.0
+        out = warp(frame, flow, variant=variant)
+        assert out.shape == frame.shape and out.is_contiguous()
+        assert maxabs(N(out), g[f"out{i}"]) <= 1e-5, (i, variant)
+
+
+@pytest.mark.parametrize("mode", ["bilinear", "nearest"])
+@pytest.mark.parametrize("pad", ["zeros", "border", "reflection"])
+@pytest.mark.parametrize("ac", [False, True])
+def test_warp_options_golden(golden, mode, pad, ac):
+    from optical_flow import warp
+
+    g = golden("warp")
+    ref = g[f"opt_{mode}_{pad}_{int(ac)}"]
+    for variant in ([1] if mode == "nearest" else [1, 2]):
+        out = N(warp(T(g["opt_frame"]), T(g["opt_flow"]), mode=mode, padding_mode=pad, align_corners=ac, variant=variant))
+        if mode == "nearest":
+            assert np.mean(out != ref) <= 0.005
+        else:
+            assert maxabs(out, ref) <= 1e-5, variant
+
+
+@pytest.mark.parametrize("shape,sigma", [((2, 3, 70, 130), 5.0), ((1, 3, 368, 496), 5.0), ((3, 5, 33, 257), 20.0), ((1, 1, 16, 64), 0.3)])
+@pytest.mark.parametrize("pad,ac", [("border", False), ("zeros", False), ("reflection", True)])
+def test_warp_vs_oracle(shape, sigma, pad, ac):
+    from optical_flow import normalize, warp
+
+    r = rng(1)
+    b, c, h, w = shape
+    frame = r.random(shape, dtype=np.float32)
+    flow_px = (sigma * r.standard_normal((b, 2, h, w))).astype(np.float32)
+    flow = oracle.normalize(flow_px).astype(np.float32)
+    ref, ref_mask = oracle.warp(frame, flow, padding_mode=pad, align_corners=ac, return_mask=True)
+    outs = []
+    for variant in (1, 2):
+        out, mask = warp(T(frame), T(flow), padding_mode=pad, align_corners=ac, return_mask=True, variant=variant)
+        assert maxabs(N(out), ref) <= 1e-5, variant
+        assert np.array_equal(N(mask).astype(np.uint8), ref_mask), variant      # validity mask bit-exact
+        outs.append(N(out))
+    assert np.array_equal(outs[0], outs[1])                                      # both kernels agree bit for bit
+    assert maxabs(N(normalize(T(flow_px))), flow) == 0.0
+
+
+def test_warp_channels_last_and_host_tensors():
+    from optical_flow import warp
+
+    r = rng(2)
+    frame = r.random((2, 8, 40, 72), dtype=np.float32)
+    flow = oracle.normalize((4 * r.standard_normal((2, 2, 40, 72))).astype(np.float32)).astype(np.float32)
+    ref = oracle.warp(frame, flow)
+    cl = T(frame).contiguous(memory_format=torch.channels_last)
+    out = warp(cl, T(flow))
+    assert out.is_contiguous() and maxabs(N(out), ref) <= 1e-5
+    cl3 = T(frame[:, :3].copy()).contiguous(memory_format=torch.channels_last)
+    assert maxabs(N(warp(cl3, T(flow))), oracle.warp(frame[:, :3].copy(), flow)) <= 1e-5
+    host = warp(torch.from_numpy(frame), torch.from_numpy(flow))       # staged through the GPU, returned on host
+    assert not host.is_cuda and maxabs(host.numpy(), ref) <= 1e-5
+
+
+def test_warp_full_size_properties():
+    """C2 32x3x436x1024: zero flow is the reference's non-identity resample; an integer pixel shift
+    (in the reference's W/(W-1) units) reproduces shifted pixels exactly; linear in the frame."""
+    from optical_flow import warp
+
+    b, c, h, w = 32, 3, 436, 1024
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    frame = torch.rand((b, c, h, w), device="cuda", generator=gen)
+    flow = torch.randn((b, 2, h, w), device="cuda", generator=gen) * 0.01
+    o1 = warp(frame, flow, variant=1)
+    o2 = warp(frame, flow, variant=2)
+    assert torch.equal(o1, o2)
+    frame2 = torch.rand((b, c, h, w), device="cuda", generator=gen)
+    lin = warp(frame + frame2, flow)
+    assert float((lin - (o1 + warp(frame2, flow))).abs().max()) <= 4e-6
+    # align_corners=True + zero flow is the identity
+    ident = warp(frame, torch.zeros_like(flow), align_corners=True)
+    assert float((ident - frame).abs().max()) <= 2e-4       # ulp(1023) = 6e-5 on the source coordinate
+    out, mask = warp(frame, torch.zeros_like(flow), return_mask=True)
+    assert int(mask.sum()) == b * (h - 2) * (w - 2)          # border pixels sit exactly on -1 / +1
+
+
+def test_warp_errors():
+    from optical_flow import scale, warp
+
+    x = torch.zeros(1, 3, 4, 4, device="cuda")
+    f = torch.zeros(1, 2, 4, 4, device="cuda")
+    with pytest.raises(NotImplementedError):
+        warp(x, f, mode="bicubic")
+    with pytest.raises(NotImplementedError):
+        warp(x.double(), f.double())
+    with pytest.raises(RuntimeError):
+        warp(x, torch.zeros(1, 2, 5, 4, device="cuda"))
+    with pytest.raises(AssertionError):
+        scale(torch.zeros(1, 3, 4, 4, device="cuda"), 2.0)
+    with pytest.raises(AssertionError):
+        scale(f, (1.0, 2.0, 3.0))
+    with pytest.raises(NotImplementedError):
+        warp(x.requires_grad_(), f).sum().backward()
+
+
+def test_warp_grid_and_integrate_golden(golden):
+    from optical_flow import integrate
+    from optical_flow.operator.operator import warp_grid
+
+    g = golden("warp")
+    grid = warp_grid(T(g["flow0"]).permute(0, 2, 3, 1).contiguous())
+    assert maxabs(N(grid), g["grid0"]) == 0.0
+    r = golden("resize")
+    out = integrate(T(r["int_f1"]), T(r["int_f2"]), T(r["int_f3"]))
+    assert maxabs(N(out), r["integrate"]) <= 1e-5
+    with pytest.raises(AssertionError):
+        integrate(T(r["int_f1"]))
+
+
+# =============================================================================== K4a resize / scale
+FLOW22 = [[[1.0, 3.0], [2.0, 4.0]], [[-1.0, -2.0], [-3.0, -4.0]]]
+
+
+def test_resize_reference_known_answers():
+    """reference tests/operator/test_operator.py:41-132 (exact, CPU tensors)."""
+    from optical_flow import resize, scale
+
+    flow = torch.tensor(FLOW22).unsqueeze(0)
+    s = scale(flow, 2)
+    assert torch.equal(s[:, 0], 2 * flow[:, 0]) and torch.equal(s[:, 1], 2 * flow[:, 1])
+    s = scale(flow, (3, -1))
+    assert torch.equal(s[:, 0], 3 * flow[:, 0]) and torch.equal(s[:, 1], -1 * flow[:, 1])
+    x = torch.tensor([[1.0, 1.5, 2.5, 3.0], [1.25, 1.75, 2.75, 3.25], [1.75, 2.25, 3.25, 3.75], [2.0, 2.5, 3.5, 4.0]])
+    y = torch.tensor([[-1.0, -1.25, -1.75, -2.0], [-1.5, -1.75, -2.25, -2.5], [-2.5, -2.75, -3.25, -3.5], [-3.0, -3.25, -3.75, -4.0]])
+    assert torch.equal(resize(flow, scale_factor=2), 2 * torch.stack([x, y]).unsqueeze(0))
+    assert torch.equal(resize(flow, size=(4, 2)), torch.stack([x[:, [0, 3]], 2 * y[:, [0, 3]]]).unsqueeze(0))
+    assert torch.equal(resize(flow, size=(2, 4)), torch.stack([2 * x[[0, 3]], y[[0, 3]]]).unsqueeze(0))
+
+
+def test_resize_golden(golden):
+    from model.utils import upflow8
+    from optical_flow import denormalize, normalize, resize, scale
+
+    g = golden("resize")
+    flow = T(g["flow"])
+    assert maxabs(N(scale(flow, 2)), g["scale_2"]) == 0.0
+    assert maxabs(N(scale(flow, (3, -1))), g["scale_3_m1"]) == 0.0
+    assert maxabs(N(normalize(flow)), g["normalize"]) == 0.0
+    assert maxabs(N(denormalize(flow)), g["denormalize"]) == 0.0
+    for key, kw in [("resize_20_31", dict(size=(20, 31))), ("resize_4_5", dict(size=(4, 5))),
+                    ("resize_9_13", dict(size=(9, 13))), ("resize_sf2", dict(scale_factor=2)),
+                    ("resize_sf2p5", dict(scale_factor=2.5)), ("resize_sf0p5", dict(scale_factor=0.5))]:
+        out = N(resize(flow, **kw))
+        assert out.shape == g[key].shape, key
+        assert maxabs(out, g[key]) <= tol(g[key]), key
+    assert maxabs(N(upflow8(T(g["small"]))), g["upflow8"]) <= tol(g["upflow8"])
+    with pytest.raises(NotImplementedError):
+        resize(flow, scale_factor=2, mode="bicubic")
+
+
+def test_resize_vs_oracle_kitti():
+    from model.utils import upflow8
+    from optical_flow import resize
+
+    r = rng(3)
+    flow = (4 * r.standard_normal((4, 2, 47, 156))).astype(np.float32)
+    ref = oracle.upflow8(flow)
+    assert maxabs(N(upflow8(T(flow))), ref) <= tol(ref)
+    ref = oracle.resize(flow, size=(375, 1242))
+    assert maxabs(N(resize(T(flow), size=(375, 1242))), ref) <= tol(ref)
+
+
+# =============================================================================== K4b convex upsample
+def test_upsample_flow_golden(golden):
+    from model.raft import RAFT
+
+    g = golden("upsample_epe")
+    out = N(RAFT.upsample_flow(T(g["flow"]), T(g["mask"])))
+    assert out.shape == g["up"].shape
+    assert maxabs(out, g["up"]) <= tol(g["up"])
+
+
+def test_upsample_flow_vs_oracle_kitti_shape():
+    from model.raft import upsample_flow
+
+    r = rng(4)
+    flow = (1.0 * r.standard_normal((2, 2, 47, 156))).astype(np.float32)
+    mask = (2.0 * r.standard_normal((2, 576, 47, 156))).astype(np.float32)
+    ref = oracle.upsample_flow(flow, mask)
+    out = N(upsample_flow(T(flow), T(mask)))
+    assert maxabs(out, ref) <= tol(ref)
+
+
+def test_upsample_flow_properties_full_size():
+    """C4 16x(2+576)x47x156: a constant flow stays constant (softmax weights sum to 1) away from the
+    zero-padded border; a one-hot mask (logit +50 on the centre tap) gives nearest upsampling * 8."""
+    from model.raft import upsample_flow
+
+    n, h, w = 16, 47, 156
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    mask = torch.randn((n, 576, h, w), device="cuda", generator=gen)
+    flow = torch.full((n, 2, h, w), 0.75, device="cuda")
+    out = upsample_flow(flow, mask)
+    inner = out[:, :, 8:-8, 8:-8]
+    assert float((inner - 6.0).abs().max()) <= 1e-5
+    flow = torch.randn((n, 2, h, w), device="cuda", generator=gen)
+    onehot = torch.zeros((n, 576, h, w), device="cuda")
+    onehot.view(n, 9, 64, h, w)[:, 4] = 50.0
+    out = upsample_flow(flow, onehot)
+    ref = 8 * flow.repeat_interleave(8, dim=2).repeat_interleave(8, dim=3)
+    assert float((out - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+
+
+# =============================================================================== K4c EPE
+def test_epe_golden(golden):
+    from optical_flow.metrics import AverageEndPointError, end_point_error
+
+    g = golden("upsample_epe")
+    pred, target, valid = T(g["pred"]), T(g["target"]), T(g["valid"])
+    assert maxabs(N(end_point_error(pred, target, reduce=False)), g["epe_map"]) <= 1e-6
+    assert abs(float(end_point_error(pred, target)) - float(g["epe_mean"])) <= 1e-6
+    m = AverageEndPointError()
+    m.update(pred, target, valid)
+    assert int(m.total) == int(g["m1_total"])
+    assert abs(float(m.sum_epe) - float(g["m1_sum"])) <= 1e-5 * float(g["m1_sum"])
+    m.update(pred * 0.5, target)
+    assert int(m.total) == int(g["m2_total"])
+    assert abs(float(m.compute()) - float(g["m2_compute"])) <= 1e-5
+
+
+@pytest.mark.parametrize("shape", [(16, 376, 1248), (3, 11, 17), (2, 1088, 1920)])
+def test_epe_vs_oracle(shape):
+    from optical_flow.metrics import AverageEndPointError
+
+    b, h, w = shape
+    r = rng(6)
+    pred = (3 * r.standard_normal((b, 2, h, w))).astype(np.float32)
+    target = (pred + r.standard_normal((b, 2, h, w))).astype(np.float32)
+    valid = (r.random((b, h, w)) > 0.1).astype(np.float32)
+    s, c = oracle.epe_sum_count(pred, target, valid)
+    m = AverageEndPointError()
+    m.update(T(pred), T(target), T(valid))
+    assert int(m.total) == c                                        # exact count
+    assert abs(float(m._acc[0]) - s) <= 1e-6 * s                    # rel <= 1e-6 on the sum
+    s2, c2 = oracle.epe_sum_count(pred, target)
+    m2 = AverageEndPointError()
+    m2.update(T(pred), T(target))
+    assert int(m2.total) == c2 == b * h * w and abs(float(m2._acc[0]) - s2) <= 1e-6 * s2
+
+
+# =============================================================================== K3 lookup
+def _pyramid_from_numpy(levels, dtype):
+    """Wrap oracle-built fp32 levels into a CorrBlock-like object that owns padded device buffers."""
+    import ctypes
+
+    import ofb200
+
+    q, _, h0, w0 = levels[0].shape
+    pyr = ofb200.Pyramid()
+    pyr.levels = len(levels)
+    pyr.dtype = ofb200.DTYPE_BF16 if dtype == torch.bfloat16 else ofb200.DTYPE_F32
+    bufs = []
+    for l, lv in enumerate(levels):
+        hl, wl = lv.shape[-2:]
+        pitch = (wl + 7) & ~7
+        buf = torch.full((q, hl, pitch), float("nan"), dtype=dtype, device="cuda")   # pads must never be read
+        buf[:, :, :wl] = T(lv[:, 0]).to(dtype)
+        bufs.append(buf)
+        pyr.base[l] = buf.data_ptr()
+        pyr.q_stride[l] = hl * pitch
+        pyr.row_pitch[l] = pitch
+        pyr.lvl_h[l] = hl
+        pyr.lvl_w[l] = wl
+    return pyr, bufs
+
+
+def _lookup(pyr, coords, radius, levels):
+    import ctypes
+
+    import ofb200
+
+    b, _, h, w = coords.shape
+    d = 2 * radius + 1
+    out = torch.empty((b, levels * d * d, h, w), device="cuda")
+    idx = torch.empty((b * h * w, levels, 2, d), dtype=torch.int32, device="cuda")
+    valid = torch.empty((b * h * w, levels, d * d), dtype=torch.uint8, device="cuda")
+    rc = ofb200.load().ofb_corr_lookup(ctypes.byref(pyr), ofb200.ptr(coords), ofb200.ptr(out), ofb200.ptr(idx),
+                                       ofb200.ptr(valid), b, h, w, radius, ofb200.stream_ptr())
+    ofb200.check(rc, "ofb_corr_lookup")
+    return N(out), N(idx), N(valid)
+
+
+@pytest.mark.parametrize("name", ["int", "noise", "far", "half"])
+def test_lookup_golden_fp32_pyramid(golden, name):
+    g = golden("corr")
+    if name in ("int", "noise"):
+        levels = [g[f"pyr{i}"] for i in range(4)]
+    else:
+        levels = [g[f"b2_pyr{i}"] for i in range(3)]
+    pyr, bufs = _pyramid_from_numpy(levels, torch.float32)
+    out, idx, valid = _lookup(pyr, T(g[f"coords_{name}"]), 4, len(levels))
+    ref = g[f"lookup_{name}"]
+    assert maxabs(out, ref) <= tol(ref)
+    assert np.array_equal(idx, g[f"idx_{name}"])                  # bit-exact
+    assert np.array_equal(valid, g[f"valid_{name}"])              # bit-exact
+
+
+def test_lookup_golden_odd_radius3(golden):
+    g = golden("corr")
+    levels = [g[f"odd_pyr{i}"] for i in range(3)]
+    pyr, bufs = _pyramid_from_numpy(levels, torch.float32)
+    out, idx, valid = _lookup(pyr, T(g["odd_coords"]), 3, 3)
+    assert maxabs(out, g["odd_lookup"]) <= tol(g["odd_lookup"])
+    assert np.array_equal(idx, g["odd_idx"]) and np.array_equal(valid, g["odd_valid"])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("hw", [(47, 156), (55, 128), (24, 40)])
+def test_lookup_vs_oracle(dtype, hw):
+    """Seeded pyramid + coords (integer coords, sub-pixel noise, far out of range) vs the oracle."""
+    h, w = hw
+    b = 1
+    r = rng(8)
+    q = b * h * w
+    levels = [r.standard_normal((q, 1, h >> l, w >> l)).astype(np.float32) for l in range(4)]
+    if dtype == torch.bfloat16:
+        levels = [oracle.round_bf16(lv) for lv in levels]          # same stored values on both sides
+    pyr, bufs = _pyramid_from_numpy(levels, dtype)
+    grid = oracle.coords_grid(b, h, w)
+    for kind in ("int", "noise", "far"):
+        coords = grid.copy()
+        if kind == "noise":
+            coords = (coords + 4 * r.standard_normal(coords.shape)).astype(np.float32)
+        if kind == "far":
+            coords = (coords + 60 * r.standard_normal(coords.shape)).astype(np.float32)
+        ref, ridx, rvalid = oracle.corr_lookup(levels, coords, radius=4, return_index=True)
+        out, idx, valid = _lookup(pyr, T(coords), 4, 4)
+        assert np.array_equal(idx, ridx), kind
+        assert np.array_equal(valid, rvalid), kind
+        assert maxabs(out, ref) <= tol(ref), kind
+
+
+def test_bilinear_sampler_golden(golden):
+    from model.utils import bilinear_sampler, coords_grid
+
+    g = golden("corr")
+    out, m = bilinear_sampler(T(g["bs_img"]), T(g["bs_pts"]), mask=True)
+    assert maxabs(N(out), g["bs_out"]) <= 1e-5
+    assert np.array_equal(N(m), g["bs_mask"])
+    assert np.array_equal(coords_grid(1, 16, 16).numpy(), g["coords_grid"])
+
+
+# =============================================================================== K2 pyramid
+def _pyr_errors(levels_gpu, levels_ref):
+    errs = []
+    for got, ref in zip(levels_gpu, levels_ref):
+        got = N(got.float())
+        assert got.shape == ref.shape
+        rel = float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
+        mx = float(np.abs(got - ref).max() / np.sqrt(np.mean(ref.astype(np.float64) ** 2)))
+        errs.append((rel, mx))
+    return errs
+
+
+@pytest.mark.parametrize("builder,dtype", [("simt", torch.float32), ("simt", torch.bfloat16)])
+def test_corr_pyramid_simt_golden(golden, builder, dtype):
+    from model.corr import CorrBlock
+
+    g = golden("corr")
+    blk = CorrBlock(T(g["fmap1"]), T(g["fmap2"]), num_levels=4, radius=4, pyramid_dtype=dtype, builder=builder)
+    refs = [g[f"pyr{i}"] for i in range(4)]
+    for (rel, mx) in _pyr_errors(blk.corr_pyramid, refs):
+        if dtype == torch.float32:
+            assert rel <= 1e-5 and mx <= 1e-4
+        else:
+            assert rel <= 4e-3 and mx <= 4e-2
+    blk = CorrBlock(T(g["odd_fmap1"]), T(g["odd_fmap2"]), num_levels=3, radius=3, pyramid_dtype=torch.float32)
+    assert [tuple(p.shape) for p in blk.corr_pyramid] == [(273, 1, 13, 21), (273, 1, 6, 10), (273, 1, 3, 5)]
+    for (rel, mx) in _pyr_errors(blk.corr_pyramid, [g[f"odd_pyr{i}"] for i in range(3)]):
+        assert rel <= 1e-5
+    out = blk(T(g["odd_coords"]))
+    assert maxabs(N(out), g["odd_lookup"]) <= 1e-4
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_corr_pyramid_tcgen05_golden(golden, cta_group):
+    """tcgen05 builder on the golden 16x16 / C=64 case (single partial tile, pooled levels clipped)."""
+    from model.corr import CorrBlock
+
+    g = golden("corr")
+    blk = CorrBlock(T(g["fmap1"]), T(g["fmap2"]), num_levels=4, radius=4, cta_group=cta_group)
+    assert blk.builder == "tcgen05"
+    torch.cuda.synchronize()
+    for (rel, mx) in _pyr_errors(blk.corr_pyramid, [g[f"pyr{i}"] for i in range(4)]):
+        assert rel <= 4e-3 and mx <= 4e-2, (rel, mx)
+    # end to end: lookup on the bf16 pyramid vs the reference's fp32 result
+    out = N(blk(T(g["coords_noise"])))
+    ref = g["lookup_noise"]
+    assert np.linalg.norm(out - ref) / np.linalg.norm(ref) <= 6e-3
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("shape", [(2, 256, 47, 156), (1, 128, 55, 128), (1, 256, 40, 72), (3, 64, 9, 35)])
+def test_corr_pyramid_tcgen05_vs_fp32(cta_group, shape):
+    """Against the fp32 CUDA-core builder (reference op order) and, for the small case, the CPU oracle."""
+    from model.corr import CorrBlock
+
+    b, c, h, w = shape
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    f1 = torch.randn(shape, device="cuda", generator=gen)
+    f2 = torch.randn(shape, device="cuda", generator=gen)
+    levels = 4 if min(h, w) >= 8 else 3
+    ref_blk = CorrBlock(f1, f2, num_levels=levels, pyramid_dtype=torch.float32, builder="simt")
+    blk = CorrBlock(f1, f2, num_levels=levels, cta_group=cta_group)
+    torch.cuda.synchronize()
+    refs = [N(p) for p in ref_blk.corr_pyramid]
+    if h * w <= 3000:
+        orc = oracle.corr_pyramid(N(f1), N(f2), levels)
+        for a, o in zip(refs, orc):
+            assert maxabs(a, o) <= 2e-4
+    for lvl, (rel, mx) in enumerate(_pyr_errors(blk.corr_pyramid, refs)):
+        assert rel <= 4e-3 and mx <= 4e-2, (lvl, rel, mx)
+
+
+def test_corr_volume_static_and_errors():
+    from model.corr import CorrBlock
+
+    gen = torch.Generator(device="cuda").manual_seed(12)
+    f1 = torch.randn((1, 64, 8, 24), device="cuda", generator=gen)
+    f2 = torch.randn((1, 64, 8, 24), device="cuda", generator=gen)
+    vol = CorrBlock.corr(f1, f2, pyramid_dtype=torch.float32)
+    assert vol.shape == (1, 8, 24, 1, 8, 24) and vol.dtype == torch.float32
+    ref = oracle.corr_volume(N(f1), N(f2))
+    assert maxabs(N(vol), ref) <= 2e-5
+    with pytest.raises(RuntimeError):
+        CorrBlock(f1[:, :, :4, :4], f2[:, :, :4, :4], num_levels=4)      # too small: reference raises too
+    with pytest.raises(RuntimeError):
+        CorrBlock(f1, f2)(torch.zeros(1, 2, 8, 23, device="cuda"))
+
+
+def test_corr_pyramid_full_size_properties():
+    """C3 B=16, 256 ch, 55x128: every pooled level equals the mean of complete 2^l x 2^l blocks of
+    level 0 (pyramid identity), checked on a random subset of queries; swapping fmap1 and fmap2
+    transposes level 0."""
+    from model.corr import CorrBlock
+
+    b, c, h, w = 16, 256, 55, 128
+    gen = torch.Generator(device="cuda").manual_seed(13)
+    f1 = torch.randn((b, c, h, w), device="cuda", generator=gen)
+    f2 = torch.randn((b, c, h, w), device="cuda", generator=gen)
+    blk = CorrBlock(f1, f2)
+    torch.cuda.synchronize()
+    q = torch.randint(0, b * h * w, (512,), device="cuda", generator=gen)
+    l0 = blk.corr_pyramid[0][q, 0].float()
+    # direct fp32 recomputation of those rows
+    qb, qp = q // (h * w), q % (h * w)
+    a = f1.view(b, c, h * w)[qb, :, qp]                                   # (512, c)
+    ref0 = torch.einsum("qc,qcn->qn", a, f2.view(b, c, h * w)[qb]) / 16.0
+    ref0 = ref0.view(-1, h, w)
+    assert float((l0 - ref0).norm() / ref0.norm()) <= 4e-3
+    for lvl in range(1, 4):
+        k = 2 ** lvl
+        hl, wl = h // k, w // k
+        pooled = ref0[:, : hl * k, : wl * k].reshape(-1, hl, k, wl, k).mean(dim=(2, 4))
+        got = blk.corr_pyramid[lvl][q, 0].float()
+        assert got.shape == pooled.shape
+        assert float((got - pooled).norm() / pooled.norm()) <= 4e-3, lvl
+    blk_t = CorrBlock(f2, f1, num_levels=1)
+    torch.cuda.synchronize()
+    bsel = 3
+    v = blk.corr_pyramid[0].view(b, h * w, h, w)[bsel].reshape(h * w, h * w).float()
+    vt = blk_t.corr_pyramid[0].view(b, h * w, h, w)[bsel].reshape(h * w, h * w).float()
+    assert float((v - vt.t()).abs().max()) <= 0.05

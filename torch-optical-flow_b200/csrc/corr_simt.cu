@@ -1,0 +1,173 @@
+// corr_simt.cu -- operand preparation for K2 and a CUDA-core correlation-pyramid builder.
+//
+//  * ofb_corr_prep_bf16: fmap (B,C,h*w) fp32 NCHW -> (B,h*w,C) bf16, K-major.  Replaces the
+//    .view / .transpose(1,2) in CorrBlock.corr (reference methods/raft/model/corr.py:82-85) and
+//    is the only extra pass the tensor-core path needs (reads 4 B, writes 2 B per element;
+//    0.17 GB at the Sintel configuration against 2.1 GB of pyramid).
+//  * ofb_pyramid_layout: strides of the pyramid buffers (see include/ofb200.h).
+//  * ofb_corr_pyramid_simt_f32: fp32 CUDA-core GEMM + successive 2x2 pooling -- the reference's
+//    own op order (corr.py:44-54,79-87).  Not the fast path: tests use it as an on-device
+//    cross-check of the tcgen05 builder at sizes the CPU oracle cannot reach.
+#include "common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------- cast + transpose
+constexpr int TP = 32;  // pixels per tile
+constexpr int TC = 64;  // channels per tile
+
+__global__ void __launch_bounds__(256) prep_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int C,
+                                                   int HW) {
+    __shared__ float tile[TC][TP + 1];
+    const int b = blockIdx.z, p0 = blockIdx.x * TP, c0 = blockIdx.y * TC;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // read: 64 channel rows x 32 pixels, each row segment one 128-byte line
+    for (int c = warp; c < TC; c += 8) {
+        const int cc = c0 + c, p = p0 + lane;
+        tile[c][lane] = (cc < C && p < HW) ? __ldg(in + ((size_t)b * C + cc) * HW + p) : 0.0f;
+    }
+    __syncthreads();
+    // write: per pixel 64 channels = 128 bytes, one bf16x2 per lane
+    for (int p = warp; p < TP; p += 8) {
+        const int pp = p0 + p, cc = c0 + 2 * lane;
+        if (pp < HW && cc < C) {
+            __nv_bfloat162 v = __floats2bfloat162_rn(tile[2 * lane][p], tile[2 * lane + 1][p]);
+            *reinterpret_cast<__nv_bfloat162*>(out + ((size_t)b * HW + pp) * C + cc) = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- fp32 GEMM (level 0)
+template <typename T> __device__ __forceinline__ T cvt_out(float v);
+template <> __device__ __forceinline__ float cvt_out<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 cvt_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+constexpr int GT = 32;
+
+template <typename T>
+__global__ void __launch_bounds__(GT * GT / 4) corr_l0_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
+                                                              T* __restrict__ l0, long long q_stride, int pitch, int C,
+                                                              int h, int w, float scale) {
+    // C[p][n] = sum_c f1[c][p] * f2[c][n]; 32x32 output tile, 8x32 threads, 4 rows per thread
+    __shared__ float sa[GT][GT + 1];
+    __shared__ float sb[GT][GT + 1];
+    const int N = h * w;
+    const int b = blockIdx.z, p0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // ty in 0..7
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k0 = 0; k0 < C; k0 += GT) {
+        for (int r = ty; r < GT; r += 8) {
+            const int c = k0 + r;
+            sa[r][tx] = (c < C && p0 + tx < N) ? __ldg(f1 + ((size_t)b * C + c) * N + p0 + tx) : 0.0f;
+            sb[r][tx] = (c < C && n0 + tx < N) ? __ldg(f2 + ((size_t)b * C + c) * N + n0 + tx) : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < GT; ++k) {
+            const float bv = sb[k][tx];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[r] = fmaf(sa[k][ty + 8 * r], bv, acc[r]);
+        }
+        __syncthreads();
+    }
+    const int n = n0 + tx;
+    if (n < N) {
+        const int y = n / w, x = n - y * w;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int p = p0 + ty + 8 * r;
+            if (p < N) l0[((size_t)b * N + p) * q_stride + (size_t)y * pitch + x] = cvt_out<T>(acc[r] * scale);
+        }
+    }
+}
+
+template <typename T> __device__ __forceinline__ float cvt_in(T v);
+template <> __device__ __forceinline__ float cvt_in<float>(float v) { return v; }
+template <> __device__ __forceinline__ float cvt_in<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) pool2_kernel(const T* __restrict__ src, T* __restrict__ dst, long long Qn,
+                                                    long long sq, int spitch, long long dq, int dpitch, int dh, int dw) {
+    const long long per = (long long)dh * dw, total = Qn * per;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long q = t / per;
+        const int r = (int)(t - q * per), y = r / dw, x = r - y * dw;
+        const T* s = src + q * sq + (size_t)(2 * y) * spitch + 2 * x;
+        float v = cvt_in<T>(s[0]);
+        v += cvt_in<T>(s[1]);
+        v += cvt_in<T>(s[spitch]);
+        v += cvt_in<T>(s[spitch + 1]);
+        dst[q * dq + (size_t)y * dpitch + x] = cvt_out<T>(v / 4.0f);
+    }
+}
+
+template <typename T>
+int build_simt(const float* f1, const float* f2, const ofb_pyramid* pyr, int B, int C, int h, int w, float scale,
+               cudaStream_t st) {
+    const int N = h * w;
+    dim3 grid((N + GT - 1) / GT, (N + GT - 1) / GT, B);
+    corr_l0_kernel<T><<<grid, GT * GT / 4, 0, st>>>(f1, f2, reinterpret_cast<T*>(pyr->base[0]), pyr->q_stride[0],
+                                                    pyr->row_pitch[0], C, h, w, scale);
+    OFB_LAUNCH_CHECK();
+    for (int l = 1; l < pyr->levels; ++l) {
+        const long long total = (long long)B * N * pyr->lvl_h[l] * pyr->lvl_w[l];
+        if (total == 0) continue;
+        long long blocks = (total + 255) / 256;
+        const int cap = ofb_num_sms() * 32;
+        if (blocks > cap) blocks = cap;
+        pool2_kernel<T><<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const T*>(pyr->base[l - 1]),
+                                                     reinterpret_cast<T*>(pyr->base[l]), (long long)B * N,
+                                                     pyr->q_stride[l - 1], pyr->row_pitch[l - 1], pyr->q_stride[l],
+                                                     pyr->row_pitch[l], pyr->lvl_h[l], pyr->lvl_w[l]);
+        OFB_LAUNCH_CHECK();
+    }
+    return OFB_OK;
+}
+
+}  // namespace
+
+OFB_API int ofb_corr_prep_bf16(const float* fmap_nchw, void* out_km_bf16, int B, int C, int HW, void* stream) {
+    if (!fmap_nchw || !out_km_bf16 || B < 0 || C <= 0 || HW <= 0) return OFB_EINVAL;
+    if (C & 1) return OFB_EUNSUPPORTED;
+    if (reinterpret_cast<uintptr_t>(out_km_bf16) & 3) return OFB_EALIGN;
+    if (B == 0) return OFB_OK;
+    if (B > 65535) return OFB_EUNSUPPORTED;
+    dim3 grid((HW + TP - 1) / TP, (C + TC - 1) / TC, B);
+    prep_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(fmap_nchw, reinterpret_cast<__nv_bfloat16*>(out_km_bf16), C, HW);
+    OFB_LAUNCH_CHECK();
+    return OFB_OK;
+}
+
+OFB_API int ofb_pyramid_layout(int h, int w, int levels, int padded, ofb_pyramid* pyr, int64_t elems[OFB_MAX_LEVELS]) {
+    if (!pyr || h <= 0 || w <= 0 || levels < 1 || levels > OFB_MAX_LEVELS) return OFB_EINVAL;
+    pyr->levels = levels;
+    for (int l = 0; l < OFB_MAX_LEVELS; ++l) {
+        pyr->base[l] = nullptr;
+        pyr->q_stride[l] = 0; pyr->row_pitch[l] = 0; pyr->lvl_h[l] = 0; pyr->lvl_w[l] = 0;
+        if (elems) elems[l] = 0;
+    }
+    for (int l = 0; l < levels; ++l) {
+        const int hl = h >> l, wl = w >> l;
+        if (hl <= 0 || wl <= 0) return OFB_EINVAL;   // F.avg_pool2d raises "Output size is too small" (corr.py:53)
+        const int pitch = padded ? ((wl + 7) & ~7) : wl;
+        pyr->lvl_h[l] = hl; pyr->lvl_w[l] = wl; pyr->row_pitch[l] = pitch;
+        pyr->q_stride[l] = (int64_t)pitch * hl;
+        if (elems) elems[l] = pyr->q_stride[l];      // per query; caller multiplies by B*h*w
+    }
+    return OFB_OK;
+}
+
+OFB_API int ofb_corr_pyramid_simt_f32(const float* fmap1, const float* fmap2, const ofb_pyramid* pyr, int B, int C,
+                                      int h, int w, float scale, void* stream) {
+    if (!fmap1 || !fmap2 || !pyr || B < 0 || C <= 0 || h <= 0 || w <= 0) return OFB_EINVAL;
+    if (pyr->levels < 1 || pyr->levels > OFB_MAX_LEVELS) return OFB_EINVAL;
+    for (int l = 0; l < pyr->levels; ++l)
+        if (!pyr->base[l] || pyr->lvl_h[l] != (h >> l) || pyr->lvl_w[l] != (w >> l) || pyr->row_pitch[l] < pyr->lvl_w[l])
+            return OFB_EINVAL;
+    if (B == 0) return OFB_OK;
+    if (B > 65535 || (h * w + GT - 1) / GT > 65535) return OFB_EUNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pyr->dtype == OFB_DTYPE_F32) return build_simt<float>(fmap1, fmap2, pyr, B, C, h, w, scale, st);
+    if (pyr->dtype == OFB_DTYPE_BF16) return build_simt<__nv_bfloat16>(fmap1, fmap2, pyr, B, C, h, w, scale, st);
+    return OFB_EINVAL;
+}

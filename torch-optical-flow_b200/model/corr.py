@@ -1,0 +1,140 @@
+"""RAFT correlation block with the reference's interface (reference methods/raft/model/corr.py),
+built by the K2 tcgen05 kernel and sampled by the K3 lookup kernel of libofb200.
+
+Differences a caller can observe, all deliberate:
+  * `corr_pyramid[l]` keeps the reference's shape (B*h*w, 1, h_l, w_l) but is a strided view of a
+    padded buffer (row pitch rounded up to 8 elements for TMA) and is stored in bf16 by default
+    (the reference's shipped configs run `precision: 16`, so its stored volume is half precision
+    too); pass `pyramid_dtype=torch.float32` for an fp32 pyramid (CUDA-core builder).
+  * forward only.
+"""
+import ctypes
+import math
+import os
+from typing import List, Optional
+
+import torch
+from torch import Tensor
+
+import ofb200
+
+
+def _default_pyramid_dtype() -> torch.dtype:
+    return torch.float32 if os.environ.get("OFB200_PYRAMID_DTYPE", "bf16").lower() in ("fp32", "f32", "float32") else torch.bfloat16
+
+
+class CorrBlock:
+    def __init__(
+        self,
+        fmap1: Tensor,
+        fmap2: Tensor,
+        num_levels: int = 4,
+        radius: int = 4,
+        *,
+        pyramid_dtype: Optional[torch.dtype] = None,
+        builder: str = "auto",
+        cta_group: int = 0,
+    ) -> None:
+        self.num_levels = num_levels
+        self.radius = radius
+        self.corr_pyramid: List[Tensor] = []
+        if fmap1.shape != fmap2.shape or fmap1.dim() != 4:
+            raise RuntimeError("CorrBlock: fmap1 and fmap2 must both be (B, C, h, w)")
+        if not (1 <= num_levels <= ofb200.MAX_LEVELS):
+            raise NotImplementedError(f"CorrBlock: num_levels must be in [1, {ofb200.MAX_LEVELS}]")
+        if pyramid_dtype is None:
+            pyramid_dtype = _default_pyramid_dtype()
+        if pyramid_dtype not in (torch.float32, torch.bfloat16):
+            raise NotImplementedError("CorrBlock: pyramid_dtype must be torch.float32 or torch.bfloat16")
+        self._on_host = not fmap1.is_cuda
+        fmap1 = ofb200.to_device(fmap1).detach()
+        fmap2 = ofb200.to_device(fmap2).detach()
+        if fmap1.dtype != torch.float32:
+            fmap1, fmap2 = fmap1.float(), fmap2.float()     # bf16 / fp16 feature maps (autocast callers)
+        fmap1, fmap2 = fmap1.contiguous(), fmap2.contiguous()
+        b, c, h, w = fmap1.shape
+        if (h >> (num_levels - 1)) == 0 or (w >> (num_levels - 1)) == 0:
+            # F.avg_pool2d in the reference: "Output size is too small" (corr.py:53)
+            raise RuntimeError("CorrBlock: feature map too small for the requested number of pyramid levels")
+        self._shape = (b, c, h, w)
+        self._dev = fmap1.device
+        lib = ofb200.load()
+        tc_ok = pyramid_dtype == torch.bfloat16 and c % 64 == 0 and c <= 256
+        if builder == "auto":
+            builder = "tcgen05" if tc_ok else "simt"
+        if builder == "tcgen05" and not tc_ok:
+            raise NotImplementedError("CorrBlock: the tcgen05 builder needs a bf16 pyramid and C in {64,128,192,256}")
+        self.builder = builder
+
+        pyr = ofb200.Pyramid()
+        elems = (ctypes.c_int64 * ofb200.MAX_LEVELS)()
+        ofb200.check(lib.ofb_pyramid_layout(h, w, num_levels, 1, ctypes.byref(pyr), ctypes.byref(elems)), "ofb_pyramid_layout")
+        pyr.dtype = ofb200.DTYPE_BF16 if pyramid_dtype == torch.bfloat16 else ofb200.DTYPE_F32
+        n = h * w
+        self._buffers = []
+        with torch.cuda.device(self._dev):
+            for lvl in range(num_levels):
+                buf = torch.empty(b * n * int(pyr.q_stride[lvl]), dtype=pyramid_dtype, device=self._dev)
+                self._buffers.append(buf)
+                pyr.base[lvl] = buf.data_ptr()
+                qs, pitch = int(pyr.q_stride[lvl]), int(pyr.row_pitch[lvl])
+                self.corr_pyramid.append(
+                    torch.as_strided(buf, (b * n, 1, int(pyr.lvl_h[lvl]), int(pyr.lvl_w[lvl])), (qs, qs, pitch, 1))
+                )
+            self._pyr = pyr
+            scale = 1.0 / math.sqrt(float(c))
+            if builder == "tcgen05":
+                a_km = torch.empty((b, n, c), dtype=torch.bfloat16, device=self._dev)
+                b_km = torch.empty((b, n, c), dtype=torch.bfloat16, device=self._dev)
+                st = ofb200.stream_ptr()
+                ofb200.check(lib.ofb_corr_prep_bf16(ofb200.ptr(fmap1), ofb200.ptr(a_km), b, c, n, st), "ofb_corr_prep_bf16")
+                ofb200.check(lib.ofb_corr_prep_bf16(ofb200.ptr(fmap2), ofb200.ptr(b_km), b, c, n, st), "ofb_corr_prep_bf16")
+                rc = lib.ofb_corr_pyramid_bf16(ofb200.ptr(a_km), ofb200.ptr(b_km), ctypes.byref(pyr), b, c, h, w,
+                                               scale, int(cta_group), st)
+                ofb200.check(rc, "ofb_corr_pyramid_bf16")
+                # keep the operands alive until the stream has consumed them
+                a_km.record_stream(torch.cuda.current_stream())
+                b_km.record_stream(torch.cuda.current_stream())
+            elif builder == "simt":
+                rc = lib.ofb_corr_pyramid_simt_f32(ofb200.ptr(fmap1), ofb200.ptr(fmap2), ctypes.byref(pyr), b, c, h, w,
+                                                   scale, ofb200.stream_ptr())
+                ofb200.check(rc, "ofb_corr_pyramid_simt_f32")
+            else:
+                raise ValueError(f"CorrBlock: unknown builder {builder!r}")
+
+    def __call__(self, coords: Tensor, return_index: bool = False):
+        """Index the pyramid (reference corr.py:56-77): coords (B, 2, h, w) -> (B, L*(2r+1)^2, h, w) fp32.
+
+        `return_index=True` (extension) also returns the floor indices (B*h*w, L, 2, 2r+1) int32 and
+        the validity mask (B*h*w, L, (2r+1)^2) uint8 the kernel used."""
+        b, c, h, w = self._shape
+        if tuple(coords.shape) != (b, 2, h, w):
+            raise RuntimeError(f"CorrBlock: coords must be {(b, 2, h, w)}, got {tuple(coords.shape)}")
+        if coords.dtype != torch.float32:
+            raise NotImplementedError("CorrBlock: coords must be fp32")
+        on_host = not coords.is_cuda
+        coords_d = ofb200.to_device(coords).detach().contiguous()
+        d = 2 * self.radius + 1
+        lvls = self.num_levels
+        with torch.cuda.device(self._dev):
+            out = torch.empty((b, lvls * d * d, h, w), dtype=torch.float32, device=self._dev)
+            idx = torch.empty((b * h * w, lvls, 2, d), dtype=torch.int32, device=self._dev) if return_index else None
+            valid = torch.empty((b * h * w, lvls, d * d), dtype=torch.uint8, device=self._dev) if return_index else None
+            rc = ofb200.load().ofb_corr_lookup(
+                ctypes.byref(self._pyr), ofb200.ptr(coords_d), ofb200.ptr(out), ofb200.ptr(idx), ofb200.ptr(valid),
+                b, h, w, self.radius, ofb200.stream_ptr(),
+            )
+        ofb200.check(rc, "ofb_corr_lookup")
+        if on_host:
+            out = out.cpu()
+            idx = idx.cpu() if idx is not None else None
+            valid = valid.cpu() if valid is not None else None
+        return (out, idx, valid) if return_index else out
+
+    @staticmethod
+    def corr(fmap1: Tensor, fmap2: Tensor, **kwargs) -> Tensor:
+        """All-pairs correlation volume (B, h, w, 1, h, w) / sqrt(C) (reference corr.py:79-87)."""
+        blk = CorrBlock(fmap1, fmap2, num_levels=1, radius=0, **kwargs)
+        b, c, h, w = blk._shape
+        vol = blk.corr_pyramid[0].reshape(b, h, w, 1, h, w).to(fmap1.dtype)
+        return vol.cpu() if blk._on_host else vol
