@@ -1,0 +1,419 @@
+#!/usr/bin/env python
+"""bench.py -- image-pairs/s of the hot path (corr + lookup, warp, EPE) on N B200s, one JSON line.
+
+Workload (BASELINE.json configs[4], "C5"): 1088x1920 image pairs, 256-channel feature maps at 1/8
+resolution (136x240), 4-level correlation pyramid, radius-4 lookup over 12 refinement iterations,
+convex 8x upsampling, backward warp + validity mask of the 3x1088x1920 frame, masked EPE, and the
+(sum, count) all-reduce over ranks.  Every rank processes `--pairs` pairs per step (8 by default, so
+8 GPUs = the config's batch of 64): weak scaling, no data-path collective.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference ...                            # the CPU path on the host cores
+
+`value`  : pairs/s with inputs resident in HBM (CUDA events, barrier + synchronize on both sides,
+           max over ranks).
+`e2e`    : pairs/s through ofb200.runner.HostStagedRunner with PINNED HOST inputs: host->device
+           copies of every input and the device->host read of the EPE state are inside the timed
+           region.
+`roofline`: the dominant kernel (K2, the tcgen05 correlation-pyramid builder) against the measured
+           peaks of MEASURED_PEAKS.json; `kernels` lists every kernel class of the pass the same way
+           and the named single-kernel configs (C2 warp, C3 corr, C4 lookup / upsample).
+`cpu_baseline`: the CPU oracle port (oracle/, C + OpenMP + numpy BLAS) on a bounded sample of the
+           same workload, timed on this box's host cores (rank 0, N=1 only).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "torch-optical-flow_b200")
+for _p in (PKG, ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "image-pairs/sec (corr+lookup, warp)"
+UNIT = "pairs/s"
+H, W, C, ITERS, RADIUS, LEVELS = 1088, 1920, 256, 12, 4, 4
+h8, w8 = H // 8, W // 8
+WORKLOAD = "c5_1080p_pipeline: fmaps 256x136x240, 4-level bf16 pyramid, r=4 lookup x12, convex upsample, warp 3x1088x1920 + mask, EPE"
+
+PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+try:
+    PEAKS.update(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))))
+    PEAKS["source"] = "measured"
+except Exception:
+    pass
+
+
+# ------------------------------------------------------------------------------ algorithmic work
+def pyramid_elems(h, w, levels=LEVELS):
+    return sum((h >> lv) * (w >> lv) for lv in range(levels))
+
+
+def algorithmic(pairs):
+    """Algorithmic bytes / flops per pass over `pairs` pairs, per kernel class."""
+    n = h8 * w8
+    d2 = (2 * RADIUS + 1) ** 2
+    return {
+        "corr_pyramid": {
+            "launches": 3,
+            "flops": 2.0 * pairs * n * n * C,
+            # fp32 fmaps read + bf16 operands written and read + bf16 pyramid written
+            "bytes": pairs * (2 * n * C * (4 + 2 + 2) + n * pyramid_elems(h8, w8) * 2),
+        },
+        "lookup": {"launches": ITERS,
+                   "bytes": ITERS * pairs * n * (LEVELS * (2 * RADIUS + 2) ** 2 * 2 + 8 + LEVELS * d2 * 4)},
+        "convex_upsample": {"launches": 1, "bytes": pairs * n * 4 * (576 + 2 + 128)},
+        "warp": {"launches": 2, "bytes": pairs * H * W * (4 * (3 + 2 + 3) + 1 + 16)},   # + normalize: 16 B/px
+        "epe": {"launches": 1, "bytes": pairs * H * W * 20},
+    }
+
+
+# ------------------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.lines, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+    def summary(self, t0, t1):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.lines:
+            if ts < t0 or ts > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, f[2:]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ synthetic inputs
+def make_batch(pairs, device, seed, torch):
+    g = torch.Generator(device=device).manual_seed(seed)
+    from model.utils import coords_grid
+
+    def rn(*s):
+        return torch.randn(s, device=device, generator=g)
+
+    base = coords_grid(pairs, h8, w8).to(device)
+    batch = {
+        "fmap1": rn(pairs, C, h8, w8), "fmap2": rn(pairs, C, h8, w8),
+        "coords": (base[None] + 4 * rn(ITERS, pairs, 2, h8, w8)).contiguous(),
+        "flow_lo": 1.5 * rn(pairs, 2, h8, w8),
+        "up_mask": rn(pairs, 576, h8, w8),
+        "frame": torch.rand((pairs, 3, H, W), device=device, generator=g),
+        "target": 12 * rn(pairs, 2, H, W),
+        "valid": (torch.rand((pairs, H, W), device=device, generator=g) > 0.1).float(),
+    }
+    batch["coords"][0] = base          # iteration 0 of RAFT looks up exact integer coordinates
+    return batch
+
+
+# ------------------------------------------------------------------------------ CPU path (oracle port)
+def cpu_pass(sample):
+    """The reference's op sequence for one pass, on the host, through the oracle port."""
+    import oracle
+
+    pyr = oracle.corr_pyramid(sample["fmap1"], sample["fmap2"], LEVELS)
+    for it in range(sample["coords"].shape[0]):
+        oracle.corr_lookup(pyr, sample["coords"][it], RADIUS)
+    flow_up = oracle.upsample_flow(sample["flow_lo"], sample["up_mask"])
+    oracle.warp(sample["frame"], oracle.normalize(flow_up), return_mask=True)
+    return oracle.epe_sum_count(flow_up, sample["target"], sample["valid"])
+
+
+def cpu_sample(pairs, seed=99):
+    import numpy as np
+
+    r = np.random.default_rng(seed)
+    ys, xs = np.meshgrid(np.arange(h8), np.arange(w8), indexing="ij")
+    base = np.stack([xs, ys], 0).astype(np.float32)[None]
+
+    def rn(*s):
+        return r.standard_normal(s, dtype=np.float32)
+
+    return {
+        "fmap1": rn(pairs, C, h8, w8), "fmap2": rn(pairs, C, h8, w8),
+        "coords": (base[None] + 4 * rn(ITERS, pairs, 2, h8, w8)).astype(np.float32),
+        "flow_lo": 1.5 * rn(pairs, 2, h8, w8), "up_mask": rn(pairs, 576, h8, w8),
+        "frame": r.random((pairs, 3, H, W), dtype=np.float32), "target": 12 * rn(pairs, 2, H, W),
+        "valid": (r.random((pairs, H, W)) > 0.1).astype(np.float32),
+    }
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def time_cpu(steps, warmup, pairs=1):
+    sample = cpu_sample(pairs)
+    for _ in range(warmup):
+        cpu_pass(sample)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_pass(sample)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": pairs / dt, "unit": UNIT, "cores": host_cores(), "kind": "port",
+            "sample": f"{pairs} pair(s) per step of the same 1080p pass (fp32 volume), {steps} timed step(s) after "
+                      f"{warmup} warm-up, oracle/ C+OpenMP+numpy-BLAS port on all host cores",
+            "s_per_pair": dt / pairs}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warm = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    cb = time_cpu(steps, warm, 1)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": cb["s_per_pair"] * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "pairs_per_step": 1, "iters": ITERS, "radius": RADIUS, "levels": LEVELS},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------ single-kernel configs
+def named_kernel_table(torch):
+    """C2 warp, C3 corr pyramid, C4 lookup x12 + convex upsample at their BASELINE.json shapes."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import microbench
+
+    recs = []
+    for fn in (microbench.bench_warp_c2, microbench.bench_corr_c3, microbench.bench_lookup_c4):
+        try:
+            recs.extend(fn())
+        except Exception as e:  # a side table must never take the headline down
+            recs.append({"kernel": fn.__name__, "error": repr(e)[:200]})
+        torch.cuda.empty_cache()
+    return recs
+
+
+# ------------------------------------------------------------------------------ main arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import ofb200
+    from ofb200.runner import FIELDS, HostStagedRunner, KernelTimers, hot_path
+    from optical_flow.metrics.epe import AverageEndPointError
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this path has no CPU fallback (use --impl reference for the CPU arm)")
+    ofb200.load()
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    if world != args.gpus and rank == 0:
+        sys.stderr.write(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}\n")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    pairs, micro = args.pairs, min(args.micro, args.pairs)
+    chunks = [(lo, min(lo + micro, pairs)) for lo in range(0, pairs, micro)]
+    batch = make_batch(pairs, device, 1234 + rank, torch)
+    views = [{k: (batch[k][:, lo:hi] if k == "coords" else batch[k][lo:hi]) for k in FIELDS} for lo, hi in chunks]
+    views = [{k: v.contiguous() for k, v in d.items()} for d in views]
+    lookup_out = torch.empty((micro, LEVELS * (2 * RADIUS + 1) ** 2, h8, w8), device=device)
+    metric = AverageEndPointError()
+
+    def step(timers=None):
+        for v in views:
+            lo = lookup_out if v["fmap1"].shape[0] == micro else None
+            hot_path(v, metric, timers=timers, lookup_out=lo, cta_group=args.cta_group)
+        metric.sync()                                  # (sum, count) all-reduce: the only collective
+
+    # ---- device-resident arm
+    for _ in range(args.warmup):
+        step()
+    metric.reset()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    timers = KernelTimers()
+    barrier()
+    l0 = ofb200.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        step(timers)
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    launches = ofb200.launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    epe_dev = float(metric.compute())
+    ksum = timers.summary()
+    value = world * pairs * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end arm: pinned host inputs, copies inside the timed region
+    host = {k: torch.empty(batch[k].shape, dtype=batch[k].dtype, pin_memory=True).copy_(batch[k]) for k in FIELDS}
+    runner = HostStagedRunner(device, min(args.e2e_micro, pairs))
+    m2 = AverageEndPointError()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    for _ in range(2):
+        runner.run(host, m2)
+    m2.reset()
+    runner.h2d_bytes = runner.d2h_bytes = 0
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(e2e_steps):
+        epe_e2e = runner.run(host, m2)
+    e1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(e0.elapsed_time(e1), wall_ms)         # host-side staging is part of the cost: take the slower clock
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * pairs * e2e_steps / (e2e_ms * 1e-3)
+    if rank == 0:
+        sampler.stop()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- rooflines
+    alg = algorithmic(micro)
+    kernels = []
+    for name, k in ksum.items():
+        a = alg[name]
+        groups = k["launches"] / a["launches"]            # passes timed
+        ms_pass = k["ms_total"] / groups
+        rec = {"kernel": name, "launches_per_pass": a["launches"], "ms_per_pass": round(ms_pass, 4),
+               "share_of_step": round(k["ms_total"] / ms, 4),
+               "gbs": round(a["bytes"] / ms_pass / 1e6, 1),
+               "hbm_frac": round(a["bytes"] / ms_pass / 1e6 / PEAKS["hbm_gbs"], 4)}
+        if "flops" in a:
+            rec["tflops"] = round(a["flops"] / ms_pass / 1e9, 1)
+            rec["tensor_frac_sustained"] = round(rec["tflops"] / PEAKS["bf16_tflops_sustained"], 4)
+        kernels.append(rec)
+    k2 = next(r for r in kernels if r["kernel"] == "corr_pyramid")
+    n = h8 * w8
+    k2_bytes = micro * (2 * n * C * 2 + n * pyramid_elems(h8, w8) * 2)   # pyramid kernel alone: bf16 operands + pyramid
+    k2_ms = ksum["corr_pyramid"]["ms_total"] / (ksum["corr_pyramid"]["launches"] / 3)
+    roofline = {
+        "kernel": "corr_pyramid_kernel (K2 tcgen05; span includes the 2 bf16 prep launches)",
+        "bound": "hbm", "achieved": round(k2_bytes / k2_ms / 1e6, 1), "peak": PEAKS["hbm_gbs"], "unit": "GB/s",
+        "frac": round(k2_bytes / k2_ms / 1e6 / PEAKS["hbm_gbs"], 4), "traffic": None,
+        "peak_source": PEAKS["source"] + " (MEASURED_PEAKS.json hbm_gbs)" if PEAKS["source"] == "measured" else "fallback",
+        "tensor": {"achieved": k2["tflops"], "peak": PEAKS["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                   "frac": k2["tensor_frac_sustained"]},
+        "note": "K=256 makes the builder write-bound: 2*N^2*C flops need 0.39 ms/pair of tensor time, the bf16 "
+                "pyramid write 0.44 ms/pair of HBM time (DESIGN.md section 4)",
+    }
+    traffic_file = os.path.join(ROOT, "profiles", "k2_traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch_at_bench_shape")
+        except Exception:
+            pass
+
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16 x bf16 -> f32 (corr), f32 (warp/lookup/upsample/EPE)",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": pairs, "global_pairs_per_step": pairs * world,
+                   "micro_batch": micro, "iters": ITERS, "radius": RADIUS, "levels": LEVELS,
+                   "l2": "inputs larger than L2 (pyramid 2.83 GB/pair, 196 MB of inputs per pair)",
+                   "parallelism": f"batch-sharded x{world}, NCCL all-reduce of (sum_epe, count) only"},
+        "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "steps": e2e_steps,
+                "h2d_bytes_per_step": runner.h2d_bytes // e2e_steps, "d2h_bytes_per_step": runner.d2h_bytes // e2e_steps,
+                "ms_per_step": round(e2e_ms / e2e_steps, 3), "micro_batch": runner.micro,
+                "api": "ofb200.runner.HostStagedRunner.run(pinned host batch) -> CorrBlock / warp / upsample_flow / AverageEndPointError -> libofb200 C ABI"},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(t_wall0, t_wall1),
+        "roofline": roofline,
+        "kernels": kernels,
+        "epe": {"device": epe_dev, "e2e": epe_e2e},
+    }
+    if world == 1 and not args.no_named:
+        line["named_configs"] = named_kernel_table(torch)
+    if world == 1 and not args.no_cpu:
+        del batch, views, host, runner
+        torch.cuda.empty_cache()
+        cb = time_cpu(1, 0, 1)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=8, help="image pairs per GPU per step")
+    ap.add_argument("--micro", type=int, default=8, help="pairs per pyramid build (device-resident arm)")
+    ap.add_argument("--e2e-micro", type=int, default=2, help="pairs per staged micro-batch (host arm)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cta-group", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-named", action="store_true", help="skip the single-kernel named configs")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3                                   # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -102,11 +102,12 @@ class CorrBlock:
             else:
                 raise ValueError(f"CorrBlock: unknown builder {builder!r}")
 
-    def __call__(self, coords: Tensor, return_index: bool = False):
+    def __call__(self, coords: Tensor, return_index: bool = False, out: Optional[Tensor] = None):
         """Index the pyramid (reference corr.py:56-77): coords (B, 2, h, w) -> (B, L*(2r+1)^2, h, w) fp32.
 
         `return_index=True` (extension) also returns the floor indices (B*h*w, L, 2, 2r+1) int32 and
-        the validity mask (B*h*w, L, (2r+1)^2) uint8 the kernel used."""
+        the validity mask (B*h*w, L, (2r+1)^2) uint8 the kernel used.  `out` (extension) is an
+        optional preallocated contiguous fp32 CUDA tensor of the output shape."""
         b, c, h, w = self._shape
         if tuple(coords.shape) != (b, 2, h, w):
             raise RuntimeError(f"CorrBlock: coords must be {(b, 2, h, w)}, got {tuple(coords.shape)}")
@@ -117,7 +118,12 @@ class CorrBlock:
         d = 2 * self.radius + 1
         lvls = self.num_levels
         with torch.cuda.device(self._dev):
-            out = torch.empty((b, lvls * d * d, h, w), dtype=torch.float32, device=self._dev)
+            oshape = (b, lvls * d * d, h, w)
+            if out is None:
+                out = torch.empty(oshape, dtype=torch.float32, device=self._dev)
+            elif (tuple(out.shape) != oshape or out.dtype != torch.float32 or not out.is_cuda
+                  or not out.is_contiguous()):
+                raise RuntimeError(f"CorrBlock: out must be a contiguous fp32 CUDA tensor of shape {oshape}")
             idx = torch.empty((b * h * w, lvls, 2, d), dtype=torch.int32, device=self._dev) if return_index else None
             valid = torch.empty((b * h * w, lvls, d * d), dtype=torch.uint8, device=self._dev) if return_index else None
             rc = ofb200.load().ofb_corr_lookup(

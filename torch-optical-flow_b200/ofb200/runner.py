@@ -1,0 +1,147 @@
+"""One pass of the hot path over a batch of image pairs, and a host-staged variant that overlaps the
+host->device copies of the next micro-batch with the kernels of the current one.
+
+The pass is the sequence the reference's RAFT.forward drives per pair (reference
+methods/raft/model/raft.py:112-142) followed by the library operators and metric it feeds
+(optical_flow/operator/operator.py:8-33, optical_flow/metrics/epe.py:25-38):
+
+    CorrBlock(fmap1, fmap2)                    K2  prep x2 + tcgen05 pyramid
+    corr_fn(coords) x iters                    K3  one launch per refinement iteration
+    RAFT.upsample_flow(flow_lo, up_mask)       K4b convex 8x upsampling
+    warp(frame, normalize(flow_up)) + mask     scale + K1
+    AverageEndPointError.update(flow_up, gt)   K4c masked sum / count
+
+The GRU update block between the lookups is out of scope, so its products
+(`coords` per iteration, `flow_lo`, `up_mask`) are inputs of the pass.
+"""
+from typing import Dict, List, Optional
+
+import torch
+from torch import Tensor
+
+from model.corr import CorrBlock
+from model.raft import upsample_flow
+from optical_flow.metrics.epe import AverageEndPointError
+from optical_flow.operator.operator import normalize, warp
+
+FIELDS = ("fmap1", "fmap2", "coords", "flow_lo", "up_mask", "frame", "target", "valid")
+
+
+class KernelTimers:
+    """CUDA-event brackets on the launching stream, one list per kernel class."""
+
+    def __init__(self) -> None:
+        self.spans: Dict[str, List] = {}
+
+    def span(self, name: str, launches: int):
+        return _Span(self, name, launches)
+
+    def summary(self) -> Dict[str, Dict[str, float]]:
+        torch.cuda.synchronize()
+        out = {}
+        for name, items in self.spans.items():
+            ms = sum(a.elapsed_time(b) for a, b, _ in items)
+            n = sum(k for _, _, k in items)
+            out[name] = {"launches": n, "ms_total": ms, "ms_per_launch": ms / max(n, 1)}
+        return out
+
+
+class _Span:
+    def __init__(self, timers: KernelTimers, name: str, launches: int) -> None:
+        self.t, self.name, self.launches = timers, name, launches
+
+    def __enter__(self):
+        self.a = torch.cuda.Event(enable_timing=True)
+        self.b = torch.cuda.Event(enable_timing=True)
+        self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        self.b.record()
+        self.t.spans.setdefault(self.name, []).append((self.a, self.b, self.launches))
+        return False
+
+
+class _NoSpan:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def hot_path(batch: Dict[str, Tensor], metric: AverageEndPointError, timers: Optional[KernelTimers] = None,
+             lookup_out: Optional[Tensor] = None, cta_group: int = 0) -> Dict[str, Tensor]:
+    """Run the pass on device tensors.  `batch["coords"]` is (iters, B, 2, h, w)."""
+    sp = (lambda n, k: timers.span(n, k)) if timers is not None else (lambda n, k: _NoSpan())
+    with sp("corr_pyramid", 3):
+        blk = CorrBlock(batch["fmap1"], batch["fmap2"], num_levels=4, radius=4, cta_group=cta_group)
+    iters = batch["coords"].shape[0]
+    corr = None
+    with sp("lookup", iters):
+        for it in range(iters):
+            corr = blk(batch["coords"][it], out=lookup_out)
+    with sp("convex_upsample", 1):
+        flow_up = upsample_flow(batch["flow_lo"], batch["up_mask"])
+    with sp("warp", 2):
+        warped, vmask = warp(batch["frame"], normalize(flow_up), return_mask=True)
+    with sp("epe", 1):
+        metric.update(flow_up, batch["target"], batch["valid"])
+    return {"corr": corr, "flow_up": flow_up, "warped": warped, "mask": vmask}
+
+
+LAUNCHES_PER_PASS = lambda iters: 3 + iters + 1 + 2 + 1  # noqa: E731  (prep x2, pyramid, lookups, upsample, scale, warp, epe)
+
+
+class HostStagedRunner:
+    """Runs the pass on PINNED HOST batches: micro-batches are copied on a side stream into two
+    alternating device slots while the previous micro-batch computes; the EPE state is read back at the
+    end.  This is the end-to-end entry point bench.py times (`e2e`)."""
+
+    def __init__(self, device: torch.device, micro_pairs: int) -> None:
+        self.device = device
+        self.micro = micro_pairs
+        self.copy_stream = torch.cuda.Stream(device=device)
+        self.slots: List[Optional[Dict[str, Tensor]]] = [None, None]
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.freed = [torch.cuda.Event(), torch.cuda.Event()]
+        self.lookup_out: Optional[Tensor] = None
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+
+    def _slice(self, host: Dict[str, Tensor], lo: int, hi: int) -> Dict[str, Tensor]:
+        return {k: (host[k][:, lo:hi] if k == "coords" else host[k][lo:hi]) for k in FIELDS}
+
+    def _stage(self, slot: int, src: Dict[str, Tensor]) -> None:
+        if self.slots[slot] is None or any(self.slots[slot][k].shape != src[k].shape for k in FIELDS):
+            self.slots[slot] = {k: torch.empty(src[k].shape, dtype=src[k].dtype, device=self.device) for k in FIELDS}
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.freed[slot])       # previous user of this slot has finished
+            for k in FIELDS:
+                self.slots[slot][k].copy_(src[k], non_blocking=True)
+                self.h2d_bytes += src[k].numel() * src[k].element_size()
+            self.ready[slot].record(self.copy_stream)
+
+    def run(self, host: Dict[str, Tensor], metric: AverageEndPointError) -> float:
+        for k in FIELDS:
+            if host[k].is_cuda or not host[k].is_pinned():
+                raise RuntimeError(f"HostStagedRunner: {k} must be a pinned host tensor")
+        pairs = host["fmap1"].shape[0]
+        chunks = [(lo, min(lo + self.micro, pairs)) for lo in range(0, pairs, self.micro)]
+        cur = torch.cuda.current_stream(self.device)
+        self._stage(0, self._slice(host, *chunks[0]))
+        for i, _ in enumerate(chunks):
+            slot = i & 1
+            if i + 1 < len(chunks):
+                self._stage(slot ^ 1, self._slice(host, *chunks[i + 1]))
+            cur.wait_event(self.ready[slot])
+            dev = self.slots[slot]
+            b, _, h, w = dev["fmap1"].shape
+            if self.lookup_out is None or self.lookup_out.shape[0] != b or self.lookup_out.shape[2:] != (h, w):
+                self.lookup_out = torch.empty((b, 324, h, w), dtype=torch.float32, device=self.device)
+            hot_path(dev, metric, lookup_out=self.lookup_out)
+            self.freed[slot].record(cur)
+        metric.sync()
+        state = metric._acc.cpu()                        # device -> host read of the step's result
+        self.d2h_bytes += state.numel() * state.element_size()
+        return float(state[0] / state[1])
