@@ -1,0 +1,84 @@
+"""CPU-side checks of the C ABI and the host shims (no kernel is launched):
+libofb200.so loads and exports every symbol include/ofb200.h declares, the ctypes table binds all of
+them, argument validation returns the documented codes, and the product path refuses to run without
+a CUDA device instead of falling back."""
+import ctypes
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import __graft_entry__ as entry  # noqa: E402
+import ofb200  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(ofb200.LIB_PATH):
+        ofb200.build()
+    return ofb200.load()
+
+
+def test_every_header_symbol_is_exported_and_bound(lib):
+    syms = entry.header_symbols()
+    assert len(syms) >= 16
+    raw = ctypes.CDLL(ofb200.LIB_PATH)
+    for s in syms:
+        assert hasattr(raw, s), f"{s} declared in include/ofb200.h but not exported"
+        assert s in ofb200.SIGNATURES, f"{s} has no ctypes signature"
+    assert lib.ofb_version() == 100
+    assert lib.ofb_strerror(0) == b"ok"
+    assert b"invalid" in lib.ofb_strerror(-1)
+
+
+def test_pyramid_layout_is_host_only(lib):
+    pyr = ofb200.Pyramid()
+    elems = (ctypes.c_int64 * ofb200.MAX_LEVELS)()
+    assert lib.ofb_pyramid_layout(47, 156, 4, 1, ctypes.byref(pyr), ctypes.byref(elems)) == 0
+    assert [pyr.lvl_h[i] for i in range(4)] == [47, 23, 11, 5]
+    assert [pyr.lvl_w[i] for i in range(4)] == [156, 78, 39, 19]       # floor: trailing odd rows / cols dropped
+    for i in range(4):
+        assert pyr.row_pitch[i] % 8 == 0 and pyr.row_pitch[i] >= pyr.lvl_w[i]
+        assert pyr.q_stride[i] % 8 == 0 and pyr.q_stride[i] >= pyr.row_pitch[i] * pyr.lvl_h[i]
+    assert lib.ofb_pyramid_layout(4, 4, 4, 1, ctypes.byref(pyr), ctypes.byref(elems)) != 0   # level 3 would be empty
+    assert lib.ofb_pyramid_layout(8, 8, 5, 1, ctypes.byref(pyr), ctypes.byref(elems)) != 0
+
+
+def test_argument_validation_without_launch(lib):
+    null = None
+    assert lib.ofb_warp_f32(null, null, null, null, 1, 3, 8, 8, 0, 1, 0, 0, 0, null) == -1
+    assert lib.ofb_convex_upsample_f32(null, null, null, 1, 4, 4, null) == -1
+    assert lib.ofb_epe_reduce_f32(null, null, null, null, 1, 4, 4, null) == -1
+    assert lib.ofb_corr_lookup(null, null, null, null, null, 1, 4, 4, 4, null) == -1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    from optical_flow import normalize, warp
+
+    with pytest.raises(ofb200.OfbError):
+        warp(torch.zeros(1, 1, 2, 2), torch.zeros(1, 2, 2, 2))
+    with pytest.raises(ofb200.OfbError):
+        normalize(torch.zeros(1, 2, 2, 2))
+    from model.corr import CorrBlock
+
+    with pytest.raises(ofb200.OfbError):
+        CorrBlock(torch.zeros(1, 64, 8, 8), torch.zeros(1, 64, 8, 8))
+
+
+def test_reference_assertion_behaviour():
+    """Shape preconditions are bare asserts, as in the reference (operator.py:74,77,105-106,128,144,160,163)."""
+    from optical_flow import denormalize, integrate, normalize, resize, scale
+
+    bad = torch.zeros(1, 3, 4, 4)
+    for fn in (scale, normalize, denormalize, resize):
+        with pytest.raises(AssertionError):
+            fn(bad)
+    with pytest.raises(AssertionError):
+        scale(torch.zeros(1, 2, 4, 4), (1.0, 2.0, 3.0))
+    with pytest.raises(AssertionError):
+        integrate(torch.zeros(1, 2, 4, 4))

@@ -145,3 +145,17 @@ class HostStagedRunner:
         state = metric._acc.cpu()                        # device -> host read of the step's result
         self.d2h_bytes += state.numel() * state.element_size()
         return float(state[0] / state[1])
+
+
+def shard_range(total: int, rank: int, world: int):
+    """Contiguous batch slice [lo, hi) of `total` pairs owned by `rank` (pairs never cross GPUs)."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world of {world}")
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_batch(batch: Dict[str, Tensor], rank: int, world: int) -> Dict[str, Tensor]:
+    lo, hi = shard_range(batch["fmap1"].shape[0], rank, world)
+    return {k: (v[:, lo:hi] if k == "coords" else v[lo:hi]) for k, v in batch.items()}
