@@ -144,6 +144,14 @@ int ofb_pyramid_layout(int h, int w, int levels, int padded, ofb_pyramid* pyr_ho
 int ofb_corr_prep_bf16(const float* fmap_nchw, void* out_km_bf16, int B, int C, int HW, void* stream);
 int ofb_corr_pyramid_bf16(const void* f1_km, const void* f2_km, const ofb_pyramid* pyr_host,
                           int B, int C, int h, int w, float scale, int cta_group, void* stream);
+/* Diagnostics build of the same kernel: additionally fills prof_dev[grid][16] (device, uint64) with
+ * per-CTA cycle counters -- [0] TMA warp waiting for a free fmap2 stage, [1] for a free fmap1 block,
+ * [2] MMA warp waiting for fmap1, [3] for a drained TMEM accumulator, [4] for fmap2 data,
+ * [5] epilogue waiting for a finished accumulator, [6] for the previous tile's TMA stores,
+ * [7] tiles done, [8] kernel cycles.  Used by tools/k2_profile.py, never by the product path. */
+int ofb_corr_pyramid_bf16_profile(const void* f1_km, const void* f2_km, const ofb_pyramid* pyr_host,
+                                  int B, int C, int h, int w, float scale, int cta_group,
+                                  uint64_t* prof_dev, void* stream);
 int ofb_corr_pyramid_simt_f32(const float* fmap1, const float* fmap2, const ofb_pyramid* pyr_host,
                               int B, int C, int h, int w, float scale, void* stream);
 

@@ -29,6 +29,8 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -69,6 +71,8 @@ struct GemmParams {
     __nv_bfloat16* l3_base;      // level 3 is stored directly
     long long l3_qs;
     int l3_pitch, l3_h, l3_w;
+    int dbg;                     // PROF builds only: bit mask disabling parts of the epilogue (tools/k2_profile.py)
+    unsigned long long* prof;    // optional per-CTA wait-cycle counters (ofb_corr_pyramid_bf16_profile)
 };
 
 // ------------------------------------------------------------------------------------ PTX helpers
@@ -110,6 +114,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > (1u << 26)) __trap();
+    }
+}
+template <bool PROF>
+__device__ __forceinline__ void mbar_wait_p(uint32_t bar, uint32_t parity, unsigned long long& acc) {
+    if (PROF) {
+        const long long t0 = clock64();
+        mbar_wait(bar, parity);
+        acc += (unsigned long long)(clock64() - t0);
+    } else {
+        mbar_wait(bar, parity);
     }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -258,7 +272,7 @@ __device__ __forceinline__ ItemCoord decode_item(const GemmParams& P, int item) 
 }
 
 // ------------------------------------------------------------------------------------ the kernel
-template <int CG>
+template <int CG, bool PROF>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_l0, const __grid_constant__ CUtensorMap map_l1,
@@ -302,6 +316,9 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const uint32_t tmem_base = *tmem_slot_gen;
 
     const int m_rows = BLOCK_M * CG;   // query rows per work item
+    const long long t_start = PROF ? clock64() : 0;
+    const int dbg = PROF ? P.dbg : 0;
+    unsigned long long pw0 = 0, pw1 = 0, pw2 = 0, ptiles = 0;   // per-role wait cycles (PROF only)
 
     if (warp == 0) {
         // ============================== TMA producer (one lane) ==============================
@@ -310,7 +327,7 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             uint32_t stage = 0, bphase = 0, aphase = 0;
             for (int item = worker; item < P.n_items; item += n_workers) {
                 const ItemCoord ic = decode_item(P, item);
-                mbar_wait(bar_a_empty, aphase ^ 1);
+                mbar_wait_p<PROF>(bar_a_empty, aphase ^ 1, pw1);
                 aphase ^= 1;
                 if (leader) mbar_expect_tx(bar_a_full, (uint32_t)(P.kb * A_KB_BYTES * CG));
                 const int row0 = ic.m * m_rows + (int)rank * BLOCK_M;
@@ -322,13 +339,17 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     const int ty = t / P.ntx, tx = t - ty * P.ntx;
                     const int x0 = tx * PATCH_W, y0 = ty * PATCH_H + (int)rank * (PATCH_H / CG);
                     for (int kb = 0; kb < P.kb; ++kb) {
-                        mbar_wait(bar_b_empty + 8 * stage, bphase ^ 1);
+                        mbar_wait_p<PROF>(bar_b_empty + 8 * stage, bphase ^ 1, pw0);
                         const uint32_t full_b = (CG == 2) ? map_to_rank(bar_b_full + 8 * stage, 0) : bar_b_full + 8 * stage;
                         if (leader) mbar_expect_tx(bar_b_full + 8 * stage, (uint32_t)B_TILE_KB_BYTES);
                         tma_load_4d<CG>(sbase + OFF_B + stage * B_STAGE_BYTES, &map_b, full_b, kb * BLOCK_K, x0, y0, ic.b);
                         if (++stage == B_STAGES) { stage = 0; bphase ^= 1; }
                     }
                 }
+            }
+            if (PROF && P.prof) {
+                unsigned long long* o = P.prof + (size_t)blockIdx.x * 16;
+                o[0] = pw0; o[1] = pw1;
             }
         }
         __syncwarp();
@@ -339,17 +360,17 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             uint32_t stage = 0, bphase = 0, aphase = 0, acc = 0, tphase = 0;
             for (int item = worker; item < P.n_items; item += n_workers) {
                 const ItemCoord ic = decode_item(P, item);
-                mbar_wait(bar_a_full, aphase);
+                mbar_wait_p<PROF>(bar_a_full, aphase, pw0);
                 aphase ^= 1;
                 tc_fence_after();
                 const int t0 = ic.chunk * P.tiles_per_item;
                 const int t1 = min(t0 + P.tiles_per_item, P.ntiles);
                 for (int t = t0; t < t1; ++t) {
-                    mbar_wait(bar_t_empty + 8 * acc, tphase ^ 1);
+                    mbar_wait_p<PROF>(bar_t_empty + 8 * acc, tphase ^ 1, pw1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * TILE_N;
                     for (int kb = 0; kb < P.kb; ++kb) {
-                        mbar_wait(bar_b_full + 8 * stage, bphase);
+                        mbar_wait_p<PROF>(bar_b_full + 8 * stage, bphase, pw2);
                         tc_fence_after();
                         const uint64_t adesc = make_smem_desc(sbase + OFF_A + kb * A_KB_BYTES);
                         const uint64_t bdesc = make_smem_desc(sbase + OFF_B + stage * B_STAGE_BYTES);
@@ -366,6 +387,10 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     if (++acc == 2) { acc = 0; tphase ^= 1; }
                 }
                 umma_commit<CG>(bar_a_empty);                          // resident A may be replaced
+            }
+            if (PROF && P.prof) {
+                unsigned long long* o = P.prof + (size_t)blockIdx.x * 16;
+                o[2] = pw0; o[3] = pw1; o[4] = pw2;
             }
         }
         __syncwarp();
@@ -385,24 +410,35 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const int t1 = min(t0 + P.tiles_per_item, P.ntiles);
             for (int t = t0; t < t1; ++t) {
                 const int ty = t / P.ntx, tx = t - ty * P.ntx;
-                mbar_wait(bar_t_full + 8 * acc, tphase);
+                mbar_wait_p<PROF>(bar_t_full + 8 * acc, tphase, pw0);
                 tc_fence_after();
-                if (store_thread) tma_store_wait_read();   // previous tile's stores have drained the stage
-                epi_bar_sync();
+                {
+                    const long long t0 = PROF ? clock64() : 0;
+                    if (store_thread) tma_store_wait_read();   // previous tile's stores have drained the stage
+                    epi_bar_sync();
+                    if (PROF) pw1 += (unsigned long long)(clock64() - t0);
+                }
+                ++ptiles;
                 const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * TILE_N;
                 float l1[2][16];     // level-1 rows of the current 4-row band
                 float l2[2][8];      // level-2 rows of the tile
 #pragma unroll
                 for (int rp = 0; rp < 4; ++rp) {           // patch rows 2rp, 2rp+1
                     uint32_t v[64];
-                    tmem_ld64(taddr + rp * 64, v);
-                    tmem_ld_wait();
+                    if (PROF && (dbg & 32)) {
+#pragma unroll
+                        for (int c = 0; c < 64; ++c) v[c] = 0x3f800000u + c;
+                    } else {
+                        tmem_ld64(taddr + rp * 64, v);
+                        tmem_ld_wait();
+                    }
                     float f[64];
 #pragma unroll
                     for (int c = 0; c < 64; ++c) f[c] = __uint_as_float(v[c]) * P.scale;
                     // level 0: two rows of 32 bf16 (64 B) -> [row][query][64 B], 16-B chunks XOR-swizzled
 #pragma unroll
                     for (int rr = 0; rr < 2; ++rr) {
+                        if (PROF && (dbg & 16)) break;
                         const uint32_t rowaddr = st0 + (uint32_t)((2 * rp + rr) * (BLOCK_M * 64) + prow * 64);
 #pragma unroll
                         for (int ch = 0; ch < 4; ++ch) {
@@ -416,7 +452,7 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
                     for (int c = 0; c < 16; ++c)
                         l1r[c] = (((f[2 * c] + f[2 * c + 1]) + f[32 + 2 * c]) + f[32 + 2 * c + 1]) * 0.25f;
-                    if (P.levels > 1) {
+                    if (P.levels > 1 && !(PROF && (dbg & 16))) {
                         const uint32_t rowaddr = st1 + (uint32_t)(rp * (BLOCK_M * 32) + prow * 32);
 #pragma unroll
                         for (int ch = 0; ch < 2; ++ch) {
@@ -430,7 +466,7 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
                         for (int c = 0; c < 8; ++c)
                             l2r[c] = (((l1[0][2 * c] + l1[0][2 * c + 1]) + l1[1][2 * c]) + l1[1][2 * c + 1]) * 0.25f;
-                        if (P.levels > 2) {
+                        if (P.levels > 2 && !(PROF && (dbg & 16))) {
                             const uint32_t a2 = st2 + (uint32_t)((rp >> 1) * (BLOCK_M * 16) + prow * 16);
                             st_shared_v4(a2, pack_bf16(l2r[0], l2r[1]), pack_bf16(l2r[2], l2r[3]),
                                          pack_bf16(l2r[4], l2r[5]), pack_bf16(l2r[6], l2r[7]));
@@ -445,7 +481,7 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     else mbar_arrive_local(bar_t_empty + 8 * acc);
                 }
                 // level 3: one 8x8 block mean per 8 columns -> 4 values, stored directly
-                if (P.levels > 3) {
+                if (P.levels > 3 && !(PROF && (dbg & 8))) {
                     float l3[4];
 #pragma unroll
                     for (int c = 0; c < 4; ++c)
@@ -467,10 +503,10 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 epi_bar_sync();
                 if (store_thread) {
                     if (row0 < P.N) {
-                        tma_store_4d(&map_l0, st0, tx * PATCH_W, row0, ty * PATCH_H, ic.b);
-                        if (P.levels > 1 && tx * 16 < (P.w >> 1) && ty * 4 < (P.h >> 1))
+                        if (!(PROF && (dbg & 1))) tma_store_4d(&map_l0, st0, tx * PATCH_W, row0, ty * PATCH_H, ic.b);
+                        if (P.levels > 1 && tx * 16 < (P.w >> 1) && ty * 4 < (P.h >> 1) && !(PROF && (dbg & 2)))
                             tma_store_4d(&map_l1, st1, tx * 16, row0, ty * 4, ic.b);
-                        if (P.levels > 2 && tx * 8 < (P.w >> 2) && ty * 2 < (P.h >> 2))
+                        if (P.levels > 2 && tx * 8 < (P.w >> 2) && ty * 2 < (P.h >> 2) && !(PROF && (dbg & 4)))
                             tma_store_4d(&map_l2, st2, tx * 8, row0, ty * 2, ic.b);
                     }
                     tma_store_commit();
@@ -479,6 +515,10 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
         }
         if (store_thread) tma_store_wait_all();
+        if (PROF && P.prof && store_thread) {
+            unsigned long long* o = P.prof + (size_t)blockIdx.x * 16;
+            o[5] = pw0; o[6] = pw1; o[7] = ptiles; o[8] = (unsigned long long)(clock64() - t_start);
+        }
         __syncwarp();
     }
 
@@ -518,12 +558,12 @@ bool encode_map(CUtensorMap* m, void* base, int rank, const uint64_t* dims, cons
     return r == CUDA_SUCCESS;
 }
 
-template <int CG>
+template <int CG, bool PROF>
 int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& m0, const CUtensorMap& m1,
                 const CUtensorMap& m2, const GemmParams& P, int grid, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        OFB_CUDA(cudaFuncSetAttribute(corr_pyramid_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
+        OFB_CUDA(cudaFuncSetAttribute(corr_pyramid_kernel<CG, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
         configured = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -538,15 +578,15 @@ int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    OFB_CUDA(cudaLaunchKernelEx(&cfg, corr_pyramid_kernel<CG>, ma, mb, m0, m1, m2, P));
+    OFB_CUDA(cudaLaunchKernelEx(&cfg, corr_pyramid_kernel<CG, PROF>, ma, mb, m0, m1, m2, P));
     OFB_LAUNCH_CHECK();
     return OFB_OK;
 }
 
 }  // namespace
 
-OFB_API int ofb_corr_pyramid_bf16(const void* f1_km, const void* f2_km, const ofb_pyramid* pyr, int B, int C, int h,
-                                  int w, float scale, int cta_group, void* stream) {
+static int corr_pyramid_impl(const void* f1_km, const void* f2_km, const ofb_pyramid* pyr, int B, int C, int h, int w,
+                             float scale, int cta_group, unsigned long long* prof, void* stream) {
     if (!f1_km || !f2_km || !pyr || B < 0 || C <= 0 || h <= 0 || w <= 0) return OFB_EINVAL;
     if (cta_group < 0 || cta_group > 2) return OFB_EINVAL;
     if (pyr->levels < 1 || pyr->levels > OFB_MAX_LEVELS) return OFB_EINVAL;
@@ -618,6 +658,28 @@ OFB_API int ofb_corr_pyramid_bf16(const void* f1_km, const void* f2_km, const of
     int grid = workers * cg;
     if ((long long)grid > n_items * cg) grid = (int)(n_items * cg);
     cudaStream_t st = (cudaStream_t)stream;
-    if (cg == 2) return launch_gemm<2>(ma, mb, ml[0], ml[1], ml[2], P, grid, st);
-    return launch_gemm<1>(ma, mb, ml[0], ml[1], ml[2], P, grid, st);
+    P.prof = prof;
+    P.dbg = 0;
+    if (prof) {
+        const char* e = getenv("OFB_K2_DBG");
+        if (e) P.dbg = atoi(e);
+    }
+    if (prof) {
+        if (cg == 2) return launch_gemm<2, true>(ma, mb, ml[0], ml[1], ml[2], P, grid, st);
+        return launch_gemm<1, true>(ma, mb, ml[0], ml[1], ml[2], P, grid, st);
+    }
+    if (cg == 2) return launch_gemm<2, false>(ma, mb, ml[0], ml[1], ml[2], P, grid, st);
+    return launch_gemm<1, false>(ma, mb, ml[0], ml[1], ml[2], P, grid, st);
+}
+
+OFB_API int ofb_corr_pyramid_bf16(const void* f1_km, const void* f2_km, const ofb_pyramid* pyr, int B, int C, int h,
+                                  int w, float scale, int cta_group, void* stream) {
+    return corr_pyramid_impl(f1_km, f2_km, pyr, B, C, h, w, scale, cta_group, nullptr, stream);
+}
+
+OFB_API int ofb_corr_pyramid_bf16_profile(const void* f1_km, const void* f2_km, const ofb_pyramid* pyr, int B, int C,
+                                          int h, int w, float scale, int cta_group, uint64_t* prof_dev, void* stream) {
+    if (!prof_dev) return OFB_EINVAL;
+    return corr_pyramid_impl(f1_km, f2_km, pyr, B, C, h, w, scale, cta_group,
+                             reinterpret_cast<unsigned long long*>(prof_dev), stream);
 }
