@@ -111,7 +111,9 @@ int ofb_epe_map_f32(const float* pred, const float* target, float* out, int B, i
  * Level l of query q = (b, y, x) is an h_l x w_l image, h_l = floor(h / 2^l):
  *     element (q, yy, xx) lives at  base[l] + q * q_stride[l] + yy * row_pitch[l] + xx
  * (strides in ELEMENTS of the pyramid dtype).  ofb_pyramid_layout fills the strides the
- * tensor-core builder needs (row_pitch multiple of 8 elements, q_stride multiple of 8) and
+ * tensor-core builder needs (row_pitch multiple of 16 elements so every row starts on a 32-byte
+ * sector, q_stride multiple of 8; the builder writes whole 8-element pieces, i.e. zeros into the
+ * row padding) and
  * returns the total element count per level through elems[l] (= B*h*w*q_stride[l]).
  * ------------------------------------------------------------------------------------- */
 typedef struct ofb_pyramid {
@@ -131,27 +133,34 @@ int ofb_pyramid_layout(int h, int w, int levels, int padded, ofb_pyramid* pyr_ho
  * (methods/raft/model/corr.py:38-54,79-87): corr[b,p,q] = sum_c f1[b,c,p] f2[b,c,q] / sqrt(C),
  * levels 1.. = 2x2 average pooling over the target (q) image, complete blocks only.
  *
- * Step 1, ofb_corr_prep_bf16: fmap (B,C,h,w) fp32 NCHW -> K-major bf16 operand (B,h*w,C)
- *         (cast + transpose in one pass; replaces the .view/.transpose of corr.py:82-85).
+ * Step 1, ofb_corr_prep_bf16: fmap (B,C,h,w) fp32 NCHW -> K-major bf16 operand
+ *         (B, (h/pool)*(w/pool), C), multiplied by `scale` and, for pool = 4, averaged over complete
+ *         4x4 blocks (cast + transpose in one pass; replaces the .view/.transpose of corr.py:82-85).
+ *         The caller preps fmap1 with scale = 1/sqrt(C) (corr.py:87) and fmap2 twice: pool = 1 and,
+ *         for pyramids with more than 2 levels, pool = 4.
  * Step 2, ofb_corr_pyramid_bf16: tcgen05/TMEM GEMM tiles fed by TMA, bf16 x bf16 -> fp32
- *         accumulate, 1/sqrt(C) scale and all pooled levels produced in the epilogue.
- *         f1_km, f2_km: (B, h*w, C) bf16 from step 1 (C multiple of 64, <= 256).
- *         pyr: layout from ofb_pyramid_layout(padded = 1), dtype BF16 or F32.
+ *         accumulate; every run writes a level and its 2x2 mean from the same accumulators:
+ *         levels 0,1 from f2_km, levels 2,3 from f2q_km (avg_pool2d is linear, corr.py:52-54).
+ *         f1_km, f2_km: (B, h*w, C) bf16; f2q_km: (B, (h/4)*(w/4), C) bf16 or NULL when
+ *         pyr->levels <= 2 (C multiple of 64, <= 256).  `scale` is applied to the accumulators
+ *         (pass 1.0f when it was folded into fmap1).
+ *         pyr: layout from ofb_pyramid_layout(padded = 1), dtype BF16.
  *         cta_group: 0 = auto, 1 = one CTA per tile, 2 = CTA pair (cta_group::2).
- * ofb_corr_pyramid_simt_f32: plain CUDA-core builder (fp32 in, fp32 out) used by tests as an
+ * ofb_corr_pyramid_simt_f32: plain CUDA-core builder (fp32 in, fp32 or bf16 out) used by tests as an
  *         on-device cross-check and for shapes the tensor-core kernel rejects.
  * ------------------------------------------------------------------------------------- */
-int ofb_corr_prep_bf16(const float* fmap_nchw, void* out_km_bf16, int B, int C, int HW, void* stream);
-int ofb_corr_pyramid_bf16(const void* f1_km, const void* f2_km, const ofb_pyramid* pyr_host,
+int ofb_corr_prep_bf16(const float* fmap_nchw, void* out_km_bf16, int B, int C, int h, int w, int pool,
+                       float scale, void* stream);
+int ofb_corr_pyramid_bf16(const void* f1_km, const void* f2_km, const void* f2q_km, const ofb_pyramid* pyr_host,
                           int B, int C, int h, int w, float scale, int cta_group, void* stream);
-/* Diagnostics build of the same kernel: additionally fills prof_dev[grid][16] (device, uint64) with
- * per-CTA cycle counters -- [0] TMA warp waiting for a free fmap2 stage, [1] for a free fmap1 block,
- * [2] MMA warp waiting for fmap1, [3] for a drained TMEM accumulator, [4] for fmap2 data,
- * [5] epilogue waiting for a finished accumulator, [6] for the previous tile's TMA stores,
- * [7] tiles done, [8] kernel cycles.  Used by tools/k2_profile.py, never by the product path. */
-int ofb_corr_pyramid_bf16_profile(const void* f1_km, const void* f2_km, const ofb_pyramid* pyr_host,
-                                  int B, int C, int h, int w, float scale, int cta_group,
-                                  uint64_t* prof_dev, void* stream);
+/* Diagnostics build of the same kernel: additionally fills prof_dev[2][148][16] (device, uint64; one
+ * slot per GEMM run) with per-CTA cycle counters -- [0] TMA warp waiting for a free fmap2 stage,
+ * [1] for a free fmap1 block, [2] MMA warp waiting for fmap1, [3] for a drained TMEM accumulator,
+ * [4] for fmap2 data, [5] epilogue waiting for a finished accumulator, [7] tiles done, [8] kernel
+ * cycles.  Used by tools/k2_profile.py, never by the product path. */
+int ofb_corr_pyramid_bf16_profile(const void* f1_km, const void* f2_km, const void* f2q_km,
+                                  const ofb_pyramid* pyr_host, int B, int C, int h, int w, float scale,
+                                  int cta_group, uint64_t* prof_dev, void* stream);
 int ofb_corr_pyramid_simt_f32(const float* fmap1, const float* fmap2, const ofb_pyramid* pyr_host,
                               int B, int C, int h, int w, float scale, void* stream);
 

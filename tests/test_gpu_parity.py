@@ -328,8 +328,11 @@ def _pyramid_from_numpy(levels, dtype):
     bufs = []
     for l, lv in enumerate(levels):
         hl, wl = lv.shape[-2:]
-        pitch = (wl + 7) & ~7
-        buf = torch.full((q, hl, pitch), float("nan"), dtype=dtype, device="cuda")   # pads must never be read
+        pitch = (wl + 15) & ~15
+        # fp32 kernel: pads must never be read (NaN).  bf16 register-tile kernel: pads may be read but must
+        # not reach the output -- the contract is "finite", so poison them with a huge finite value
+        poison = float("nan") if dtype == torch.float32 else 3.0e38
+        buf = torch.full((q, hl, pitch), poison, dtype=dtype, device="cuda")
         buf[:, :, :wl] = T(lv[:, 0]).to(dtype)
         bufs.append(buf)
         pyr.base[l] = buf.data_ptr()
@@ -393,12 +396,22 @@ def test_lookup_vs_oracle(dtype, hw):
         levels = [oracle.round_bf16(lv) for lv in levels]          # same stored values on both sides
     pyr, bufs = _pyramid_from_numpy(levels, dtype)
     grid = oracle.coords_grid(b, h, w)
-    for kind in ("int", "noise", "far"):
+    for kind in ("int", "noise", "far", "half", "edge", "nonfinite"):
         coords = grid.copy()
         if kind == "noise":
             coords = (coords + 4 * r.standard_normal(coords.shape)).astype(np.float32)
         if kind == "far":
             coords = (coords + 60 * r.standard_normal(coords.shape)).astype(np.float32)
+        if kind == "half":
+            coords = (coords + 0.5).astype(np.float32)
+        if kind == "edge":          # windows hanging over every border, plus exact integers at the corners
+            coords[:, 0] = np.where(coords[:, 0] < w / 2, coords[:, 0] * 0.1 - 3.0, w - 1 + coords[:, 0] * 0.05)
+            coords[:, 1] = np.where(coords[:, 1] < h / 2, -2.0, h + 1.25)
+            coords = coords.astype(np.float32)
+        if kind == "nonfinite":
+            coords = coords.astype(np.float32)
+            coords[:, 0, ::3, ::5] = np.float32(1e9)
+            coords[:, 1, 1::4, 2::7] = np.float32(-3e7)
         ref, ridx, rvalid = oracle.corr_lookup(levels, coords, radius=4, return_index=True)
         out, idx, valid = _lookup(pyr, T(coords), 4, 4)
         assert np.array_equal(idx, ridx), kind

@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.join(ROOT, "torch-optical-flow_b200"))
 import torch  # noqa: E402
 
 import ofb200  # noqa: E402
-from model.corr import CorrBlock  # noqa: E402
+from model.corr import CorrBlock, prepare_operands  # noqa: E402
 from model.utils import coords_grid  # noqa: E402
 from optical_flow import normalize  # noqa: E402
 
@@ -97,20 +97,18 @@ def bench_corr(name, b, c, h, w, cta_groups=(0,), prep=True):
     lib = ofb200.load()
     gen, f1, f2 = _corr_setup(b, c, h, w)
     n = h * w
-    a_km = torch.empty((b, n, c), dtype=torch.bfloat16, device="cuda")
-    b_km = torch.empty((b, n, c), dtype=torch.bfloat16, device="cuda")
     st = ofb200.stream_ptr()
     recs = []
-    ms = timeit(lambda: (lib.ofb_corr_prep_bf16(ofb200.ptr(f1), ofb200.ptr(a_km), b, c, n, st),
-                         lib.ofb_corr_prep_bf16(ofb200.ptr(f2), ofb200.ptr(b_km), b, c, n, st)))
+    a_km, b_km, q_km = prepare_operands(f1, f2, 4)
+    ms = timeit(lambda: prepare_operands(f1, f2, 4))
     if prep:
-        recs.append(record(f"{name} K2 prep (both fmaps)", ms, nbytes=2 * b * c * n * 6))
+        recs.append(record(f"{name} K2 prep (fmap1, fmap2, fmap2/4x4)", ms, nbytes=b * c * n * (3 * 4 + 2 * 2 + 2 / 16)))
     blk = CorrBlock(f1, f2)
     elems = sum(int(blk._pyr.lvl_h[lv]) * int(blk._pyr.lvl_w[lv]) for lv in range(4)) * b * n
     for cg in cta_groups:
         def run():
-            rc = lib.ofb_corr_pyramid_bf16(ofb200.ptr(a_km), ofb200.ptr(b_km), ctypes.byref(blk._pyr), b, c, h, w,
-                                           1.0 / math.sqrt(c), cg, st)
+            rc = lib.ofb_corr_pyramid_bf16(ofb200.ptr(a_km), ofb200.ptr(b_km), ofb200.ptr(q_km), ctypes.byref(blk._pyr),
+                                           b, c, h, w, 1.0, cg, st)
             assert rc == 0
         ms = timeit(run, reps=10)
         recs.append(record(f"{name} K2 corr pyramid cta_group={cg}", ms, nbytes=elems * 2 + 2 * b * n * c * 2,

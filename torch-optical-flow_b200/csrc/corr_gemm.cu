@@ -1,31 +1,33 @@
-// corr_gemm.cu -- K2: all-pairs correlation pyramid on the 5th-generation tensor cores.
+// corr_gemm.cu -- K2: all-pairs correlation pyramid on the 5th-generation tensor cores (version 2).
 //
 // Replaces CorrBlock.corr + CorrBlock.__init__ (reference methods/raft/model/corr.py:38-54,79-87):
 //     corr[b,p,q] = sum_c f1[b,c,p] * f2[b,c,q] / sqrt(C)          (torch.matmul + full-volume divide)
 //     level l     = 2x2 average pooling of level l-1 over the target image, complete blocks only
-// The reference makes one cuBLAS launch plus 4 further full passes over a multi-GB volume.  Here
-// ONE persistent kernel produces every level:
+// The reference makes one cuBLAS launch plus 4 further full passes over a multi-GB volume.  Here one
+// persistent kernel produces a level AND its 2x2-pooled successor straight from the accumulators; it
+// runs twice: on fmap2 (levels 0, 1) and on the 4x4-averaged fmap2 (levels 2, 3) -- pooling is linear,
+// avgpool4(f1^T f2) = f1^T avgpool4(f2), and the second run costs 1/16 of the first.
 //
-//   * operands are K-major bf16 (ofb_corr_prep_bf16), fetched by TMA with 128-byte swizzle;
-//   * a CTA owns 128 queries (rows of the volume).  Their 128 x C slice of fmap1 stays RESIDENT in
-//     shared memory while the CTA walks target tiles; only fmap2 streams (and hits L2: every CTA
-//     walks the same tiles at the same time);
-//   * a target tile is a SPATIAL PATCH of 8 rows x 32 columns of the h x w target image, fetched with
-//     a 4-D tensor map (C, x, y, b): 256 accumulator columns, column n = 32*row + col.  TMA zero-fills
-//     out-of-image elements, so edge tiles need no masking;
-//   * tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) accumulates 128 x 256 in TMEM; two accumulator
-//     stages (2 x 256 of the 512 columns) let the epilogue of tile n overlap the MMAs of tile n+1;
-//   * with cta_group = 2 a CTA PAIR shares each target tile (each CTA loads half of it, the MMA is
-//     M = 256 across the pair), halving the L2 -> SM operand traffic per flop;
-//   * epilogue: each thread owns one query row; because a tile is a patch, the 2x2, 4x4 and 8x8
-//     means over the target image are sums of registers of ONE thread -- no shuffles, no re-read of
-//     level 0.  1/sqrt(C) is applied to the fp32 accumulator, levels 0..2 go through a swizzled
-//     shared-memory stage and leave as TMA tensor stores (which also clip to floor(h/2^l) x
-//     floor(w/2^l): the reference's "complete blocks only" rule for free), level 3 (4 values per
-//     thread and tile) is stored directly.
+//   * operands are K-major bf16 (ofb_corr_prep_bf16: cast + transpose, 1/sqrt(C) folded into fmap1),
+//     fetched by TMA with 128-byte swizzle;
+//   * a CTA owns 128 queries (rows of the volume): their 128 x C slice of fmap1 stays RESIDENT in
+//     shared memory while the CTA walks target tiles; only fmap2 streams through a 3..7 stage ring;
+//   * a target tile is 256 targets laid out as 4 "chunks" of 2 rows x 32 columns of the target image
+//     (tile shape 32x8, 64x4 or 128x2, whichever wastes least for the image width), fetched as 4-D TMA
+//     boxes (C, x, y, b).  TMA zero-fills outside the image;
+//   * tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) accumulates 128 x 256 in TMEM, two accumulator
+//     stages (2 x 256 of the 512 columns) so the epilogue of tile n overlaps the MMAs of tile n+1;
+//   * cta_group = 2: a CTA PAIR shares each target tile (each CTA loads half of it, the MMA is M = 256
+//     across the pair) -- halves the L2 -> SM operand traffic, which is what bounds cta_group = 1
+//     (measured: 37 B/cycle/SM, profiles/r01_k2_findings.md);
+//   * epilogue: 8 warps; a thread owns one query row and one 64-column chunk at a time
+//     (tcgen05.ld 32x32b.x64).  A chunk is 2 image rows x 32 columns, so the 2x2 means are sums of
+//     registers of ONE thread.  Output leaves through the LSU, not TMA (TMA tensor stores cost ~5
+//     cycles per box row and these rows are 64 bytes): each warp transposes its 32 x 128 B through a
+//     private XOR-swizzled shared-memory stage and writes 16-byte pieces, 4 lanes per 64-byte segment.
 //
-// Roofline: 2*B*N^2*C flops against the bf16 tensor peak, and
-// 2 bytes * 1.33 * B*N^2 of pyramid writes against HBM -- at C = 256 the two are within 15 %.
+// Roofline: 2*B*N^2*C flops against the bf16 tensor peak and 2 bytes * 1.33 *
+// B*N^2 of pyramid writes against HBM; at C = 256 and 1965 MHz the write is the larger bound.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -36,41 +38,53 @@
 namespace {
 
 constexpr int BLOCK_M = 128;
-constexpr int PATCH_W = 32, PATCH_H = 8;
-constexpr int TILE_N = PATCH_W * PATCH_H;   // 256 accumulator columns
+constexpr int TILE_N = 256;                 // accumulator columns = 4 chunks x (2 rows x 32 cols)
+constexpr int CHUNK = 64;
 constexpr int BLOCK_K = 64;                 // one 128-byte swizzle span of bf16
 constexpr int UMMA_K = 16;
 constexpr int MAX_KB = 4;                   // C <= 256
 constexpr int A_KB_BYTES = BLOCK_M * BLOCK_K * 2;          // 16 KiB
 constexpr int B_TILE_KB_BYTES = TILE_N * BLOCK_K * 2;      // 32 KiB per k-block for a whole tile
-constexpr int B_RING_BYTES = 64 * 1024;                    // 2 stages (cta_group 1) / 4 stages (cta_group 2)
-constexpr int ST_L0_BYTES = PATCH_H * BLOCK_M * 64;        // [8][128][64 B]   64 KiB
-constexpr int ST_L1_BYTES = (PATCH_H / 2) * BLOCK_M * 32;  // [4][128][32 B]   16 KiB
-constexpr int ST_L2_BYTES = (PATCH_H / 4) * BLOCK_M * 16;  // [2][128][16 B]    4 KiB
-constexpr int NUM_THREADS = 192;            // warp 0: TMA, warp 1: MMA + TMEM, warps 2..5: epilogue
-constexpr int NUM_EPI_WARPS = 4;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;       // warp 0: TMA, warp 1: MMA + TMEM, warps 2..9: epilogue
 constexpr int TMEM_COLS = 512;
+constexpr int MAX_STAGES = 8;
+constexpr int PROF_SLOT = 148 * 16;         // uint64 counters per GEMM run in the diagnostics buffer
+
+constexpr int STG_A_BYTES = 32 * 128;       // per warp: 32 queries x (2 rows x 32 bf16)
+constexpr int STG_B_BYTES = 32 * 32;        // per warp: 32 queries x 16 bf16 (pooled)
+constexpr int STG_WARP_BYTES = STG_A_BYTES + STG_B_BYTES;
 
 constexpr int OFF_A = 0;
-constexpr int OFF_B = OFF_A + MAX_KB * A_KB_BYTES;
-constexpr int OFF_ST0 = OFF_B + B_RING_BYTES;
-constexpr int OFF_ST1 = OFF_ST0 + ST_L0_BYTES;
-constexpr int OFF_ST2 = OFF_ST1 + ST_L1_BYTES;
-constexpr int OFF_BAR = OFF_ST2 + ST_L2_BYTES;
-constexpr int NUM_BARS = 2 + 4 + 4 + 2 + 2;   // a_full, a_empty, b_full[4], b_empty[4], t_full[2], t_empty[2]
-constexpr int SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16;
-constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;  // manual 1024-byte alignment of the dynamic segment
+constexpr int OFF_B = OFF_A + MAX_KB * A_KB_BYTES;         // 64 KiB, 1024-aligned
+template <int CG> struct Ring {
+    static constexpr int STAGE_BYTES = B_TILE_KB_BYTES / CG;              // 32 KiB / 16 KiB
+    static constexpr int STAGES = CG == 1 ? 3 : 7;                         // 96 KiB / 112 KiB
+    static constexpr int OFF_STG = OFF_B + STAGES * STAGE_BYTES;
+    static constexpr int OFF_BAR = OFF_STG + NUM_EPI_WARPS * STG_WARP_BYTES;
+    static constexpr int NUM_BARS = 2 + 2 * MAX_STAGES + 4;                // a_full, a_empty, b_full[], b_empty[], t_full[2], t_empty[2]
+    static constexpr int SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16;
+    static constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;                   // manual 1024-byte alignment of the dynamic segment
+};
+static_assert(Ring<1>::SMEM_ALLOC <= 232448 && Ring<2>::SMEM_ALLOC <= 232448, "shared memory budget");
+
+struct LevelOut {
+    __nv_bfloat16* base;
+    long long q_stride;
+    int pitch, h, w;
+};
 
 struct GemmParams {
-    int B, C, h, w, N;           // N = h*w
-    int levels;
-    int kb;                      // C / 64
-    int ntx, nty, ntiles;        // target tiles
+    int B, C, kb;
+    int Nq;                      // queries per batch element (rows of the volume)
+    int th, tw;                  // target image of THIS run (h x w, or h/4 x w/4 for the pooled run)
+    int XH, PH;                  // tile = (32*XH) x PH targets, XH*PH = 8
+    int nbox, box_rows;          // TMA boxes per stage and CTA, rows per box
+    int ntx, nty, ntiles;
     int tiles_per_item, n_chunks, mblk, n_items;
     float scale;
-    __nv_bfloat16* l3_base;      // level 3 is stored directly
-    long long l3_qs;
-    int l3_pitch, l3_h, l3_w;
+    int apply_scale, has_b;
+    LevelOut la, lb;             // level written from the accumulators, and its 2x2 mean
     int dbg;                     // PROF builds only: bit mask disabling parts of the epilogue (tools/k2_profile.py)
     unsigned long long* prof;    // optional per-CTA wait-cycle counters (ofb_corr_pyramid_bf16_profile)
 };
@@ -127,7 +141,6 @@ __device__ __forceinline__ void mbar_wait_p(uint32_t bar, uint32_t parity, unsig
     }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -138,40 +151,39 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return r;
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory"); }
 
 // TMA loads: the completion bytes are credited to `bar` (a shared::cluster address: for a CTA pair the
 // leader's barrier collects both CTAs' loads).
+// The operands are re-read by every CTA: keep them in L2 (evict_last) against the streaming pyramid writes.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 template <int CG>
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            uint64_t pol) {
     if (CG == 1)
         asm volatile(
-            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-            ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+            ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(pol) : "memory");
     else
         asm volatile(
-            "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-            ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+            "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+            ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(pol) : "memory");
 }
 template <int CG>
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3) {
+                                            int c3, uint64_t pol) {
     if (CG == 1)
         asm volatile(
-            "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-            ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+            "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+            ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol) : "memory");
     else
         asm volatile(
-            "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-            ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+            "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+            ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol) : "memory");
 }
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
 }
@@ -258,7 +270,15 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
+    return r;
+}
+// streaming (evict-first) 16-byte store: the volume is written once and must not push fmap2 out of L2
+__device__ __forceinline__ void st_global_v4(void* p, uint4 v) {
+    asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 struct ItemCoord {
     int b, chunk, m;
 };
@@ -275,22 +295,22 @@ __device__ __forceinline__ ItemCoord decode_item(const GemmParams& P, int item) 
 template <int CG, bool PROF>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    const __grid_constant__ CUtensorMap map_l0, const __grid_constant__ CUtensorMap map_l1,
-                    const __grid_constant__ CUtensorMap map_l2, const GemmParams P) {
+                    const GemmParams P) {
+    using R = Ring<CG>;
     extern __shared__ uint8_t smem_raw[];
     // the 128-byte swizzle is a function of the absolute shared address: align the segment to 1024
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t sbase = (raw + 1023u) & ~1023u;
     uint8_t* sgen = smem_raw + (sbase - raw);
-    constexpr int B_STAGE_BYTES = B_TILE_KB_BYTES / CG;
-    constexpr int B_STAGES = B_RING_BYTES / B_STAGE_BYTES;
+    constexpr int B_STAGE_BYTES = R::STAGE_BYTES;
+    constexpr int B_STAGES = R::STAGES;
 
-    const uint32_t bar0 = sbase + OFF_BAR;
+    const uint32_t bar0 = sbase + R::OFF_BAR;
     const uint32_t bar_a_full = bar0, bar_a_empty = bar0 + 8;
-    const uint32_t bar_b_full = bar0 + 16, bar_b_empty = bar0 + 16 + 32;
-    const uint32_t bar_t_full = bar0 + 80, bar_t_empty = bar0 + 96;
-    const uint32_t tmem_slot = bar0 + NUM_BARS * 8;
-    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sgen + OFF_BAR + NUM_BARS * 8);
+    const uint32_t bar_b_full = bar0 + 16, bar_b_empty = bar0 + 16 + 8 * MAX_STAGES;
+    const uint32_t bar_t_full = bar0 + 16 + 16 * MAX_STAGES, bar_t_empty = bar_t_full + 16;
+    const uint32_t tmem_slot = bar0 + R::NUM_BARS * 8;
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sgen + R::OFF_BAR + R::NUM_BARS * 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
@@ -299,10 +319,9 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_a); prefetch_tmap(&map_b);
-        prefetch_tmap(&map_l0); prefetch_tmap(&map_l1); prefetch_tmap(&map_l2);
         mbar_init(bar_a_full, 1);
         mbar_init(bar_a_empty, 1);
-        for (int s = 0; s < 4; ++s) { mbar_init(bar_b_full + 8 * s, 1); mbar_init(bar_b_empty + 8 * s, 1); }
+        for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(bar_b_full + 8 * s, 1); mbar_init(bar_b_empty + 8 * s, 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(bar_t_full + 8 * s, 1); mbar_init(bar_t_empty + 8 * s, NUM_EPI_WARPS * CG); }
         fence_barrier_init();
     }
@@ -324,6 +343,11 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         // ============================== TMA producer (one lane) ==============================
         if (lane == 0) {
             const uint32_t full_a = (CG == 2) ? map_to_rank(bar_a_full, 0) : bar_a_full;
+            // which part of the tile this CTA fetches (cta_group 2: chunks {2*rank, 2*rank+1})
+            const int xh0 = (CG == 2 && P.XH >= 2) ? (int)rank * (P.XH / 2) : 0;
+            const int yoff = (CG == 2 && P.XH == 1) ? (int)rank * (P.PH / 2) : 0;
+            const int box_bytes = 32 * P.box_rows * 128;
+            const uint64_t pol = l2_policy_evict_last();
             uint32_t stage = 0, bphase = 0, aphase = 0;
             for (int item = worker; item < P.n_items; item += n_workers) {
                 const ItemCoord ic = decode_item(P, item);
@@ -332,17 +356,19 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 if (leader) mbar_expect_tx(bar_a_full, (uint32_t)(P.kb * A_KB_BYTES * CG));
                 const int row0 = ic.m * m_rows + (int)rank * BLOCK_M;
                 for (int kb = 0; kb < P.kb; ++kb)
-                    tma_load_3d<CG>(sbase + OFF_A + kb * A_KB_BYTES, &map_a, full_a, kb * BLOCK_K, row0, ic.b);
+                    tma_load_3d<CG>(sbase + OFF_A + kb * A_KB_BYTES, &map_a, full_a, kb * BLOCK_K, row0, ic.b, pol);
                 const int t0 = ic.chunk * P.tiles_per_item;
                 const int t1 = min(t0 + P.tiles_per_item, P.ntiles);
                 for (int t = t0; t < t1; ++t) {
                     const int ty = t / P.ntx, tx = t - ty * P.ntx;
-                    const int x0 = tx * PATCH_W, y0 = ty * PATCH_H + (int)rank * (PATCH_H / CG);
+                    const int x0 = (tx * P.XH + xh0) * 32, y0 = ty * P.PH + yoff;
                     for (int kb = 0; kb < P.kb; ++kb) {
                         mbar_wait_p<PROF>(bar_b_empty + 8 * stage, bphase ^ 1, pw0);
                         const uint32_t full_b = (CG == 2) ? map_to_rank(bar_b_full + 8 * stage, 0) : bar_b_full + 8 * stage;
                         if (leader) mbar_expect_tx(bar_b_full + 8 * stage, (uint32_t)B_TILE_KB_BYTES);
-                        tma_load_4d<CG>(sbase + OFF_B + stage * B_STAGE_BYTES, &map_b, full_b, kb * BLOCK_K, x0, y0, ic.b);
+                        const uint32_t dst = sbase + OFF_B + stage * B_STAGE_BYTES;
+                        for (int j = 0; j < P.nbox; ++j)
+                            tma_load_4d<CG>(dst + j * box_bytes, &map_b, full_b, kb * BLOCK_K, x0 + 32 * j, y0, ic.b, pol);
                         if (++stage == B_STAGES) { stage = 0; bphase ^= 1; }
                     }
                 }
@@ -395,131 +421,126 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
         __syncwarp();
     } else {
-        // ============================== epilogue (4 warps, one query row per thread) =========
-        const int q4 = warp & 3;                       // TMEM lane quarter this warp may read
-        const int prow = q4 * 32 + lane;               // row inside the CTA's 128-row block
-        const bool store_thread = (warp == 2 && lane == 0);
-        const uint32_t st0 = sbase + OFF_ST0, st1 = sbase + OFF_ST1, st2 = sbase + OFF_ST2;
-        const uint32_t sw0 = (uint32_t)((prow >> 1) & 3);   // SWIZZLE_64B : 16-B chunk index ^= addr bits [7,9)
-        const uint32_t sw1 = (uint32_t)((prow >> 2) & 1);   // SWIZZLE_32B : 16-B chunk index ^= addr bit 7
+        // ============================== epilogue (8 warps) ===================================
+        // warp -> TMEM lane quarter (hardware rule: warp_id % 4) and column half; thread -> one query row
+        const int q4 = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const uint32_t stg_a = sbase + R::OFF_STG + (warp - 2) * STG_WARP_BYTES;
+        const uint32_t stg_b = stg_a + STG_A_BYTES;
+        const int ypairs = P.PH >> 1;
+        // write side of the transposes: this lane's query row, 16-byte pieces XOR-swizzled
+        const uint32_t wa = stg_a + (uint32_t)lane * 128u, wsw_a = (uint32_t)(lane & 7);
+        const uint32_t wb = stg_b + (uint32_t)lane * 32u, wsw_b = (uint32_t)((lane >> 2) & 1);
+        // read side: level A -- 8 lanes per query (2 rows x 4 pieces), 4 queries per instruction
+        const int ra_q = lane >> 3, ra_p = lane & 7;
+        // level B -- 2 lanes per query, 16 queries per instruction
+        const int rb_q = lane >> 1, rb_p = lane & 1;
         uint32_t acc = 0, tphase = 0;
         for (int item = worker; item < P.n_items; item += n_workers) {
             const ItemCoord ic = decode_item(P, item);
-            const int row0 = ic.m * m_rows + (int)rank * BLOCK_M;
+            const int qrow0 = ic.m * m_rows + (int)rank * BLOCK_M + q4 * 32;   // first query row of this warp
+            const long long qglob0 = (long long)ic.b * P.Nq + qrow0;
             const int t0 = ic.chunk * P.tiles_per_item;
             const int t1 = min(t0 + P.tiles_per_item, P.ntiles);
             for (int t = t0; t < t1; ++t) {
                 const int ty = t / P.ntx, tx = t - ty * P.ntx;
                 mbar_wait_p<PROF>(bar_t_full + 8 * acc, tphase, pw0);
                 tc_fence_after();
-                {
-                    const long long t0 = PROF ? clock64() : 0;
-                    if (store_thread) tma_store_wait_read();   // previous tile's stores have drained the stage
-                    epi_bar_sync();
-                    if (PROF) pw1 += (unsigned long long)(clock64() - t0);
-                }
-                ++ptiles;
-                const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * TILE_N;
-                float l1[2][16];     // level-1 rows of the current 4-row band
-                float l2[2][8];      // level-2 rows of the tile
+                if (PROF) ++ptiles;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + acc * TILE_N + (uint32_t)half * 2 * CHUNK;
 #pragma unroll
-                for (int rp = 0; rp < 4; ++rp) {           // patch rows 2rp, 2rp+1
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int k = half * 2 + cc;
                     uint32_t v[64];
                     if (PROF && (dbg & 32)) {
 #pragma unroll
                         for (int c = 0; c < 64; ++c) v[c] = 0x3f800000u + c;
                     } else {
-                        tmem_ld64(taddr + rp * 64, v);
+                        tmem_ld64(taddr + cc * CHUNK, v);
                         tmem_ld_wait();
                     }
+                    if (cc == 1) {
+                        // both chunks of this warp have left TMEM: hand the accumulator stage back
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (CG == 2) mbar_arrive_cluster(bar_t_empty + 8 * acc, 0);
+                            else mbar_arrive_local(bar_t_empty + 8 * acc);
+                        }
+                    }
                     float f[64];
+                    if (P.apply_scale) {
 #pragma unroll
-                    for (int c = 0; c < 64; ++c) f[c] = __uint_as_float(v[c]) * P.scale;
-                    // level 0: two rows of 32 bf16 (64 B) -> [row][query][64 B], 16-B chunks XOR-swizzled
+                        for (int c = 0; c < 64; ++c) f[c] = __uint_as_float(v[c]) * P.scale;
+                    } else {
 #pragma unroll
-                    for (int rr = 0; rr < 2; ++rr) {
-                        if (PROF && (dbg & 16)) break;
-                        const uint32_t rowaddr = st0 + (uint32_t)((2 * rp + rr) * (BLOCK_M * 64) + prow * 64);
+                        for (int c = 0; c < 64; ++c) f[c] = __uint_as_float(v[c]);
+                    }
+                    // ---- registers -> swizzled stage.  chunk = 2 image rows x 32 columns, piece p = 8 bf16
+                    if (!(PROF && (dbg & 16))) {
 #pragma unroll
-                        for (int ch = 0; ch < 4; ++ch) {
-                            const float* s = f + rr * 32 + ch * 8;
-                            st_shared_v4(rowaddr + ((ch ^ sw0) << 4), pack_bf16(s[0], s[1]), pack_bf16(s[2], s[3]),
+                        for (int p = 0; p < 8; ++p) {
+                            const float* s = f + p * 8;
+                            st_shared_v4(wa + ((p ^ wsw_a) << 4), pack_bf16(s[0], s[1]), pack_bf16(s[2], s[3]),
                                          pack_bf16(s[4], s[5]), pack_bf16(s[6], s[7]));
                         }
-                    }
-                    // level 1: 2x2 means, summed in the reference's raster order then / 4 (corr.py:53)
-                    float* l1r = l1[rp & 1];
+                        if (P.has_b) {
+                            // 2x2 means, summed in the reference's raster order then / 4 (corr.py:53)
+                            float m[16];
 #pragma unroll
-                    for (int c = 0; c < 16; ++c)
-                        l1r[c] = (((f[2 * c] + f[2 * c + 1]) + f[32 + 2 * c]) + f[32 + 2 * c + 1]) * 0.25f;
-                    if (P.levels > 1 && !(PROF && (dbg & 16))) {
-                        const uint32_t rowaddr = st1 + (uint32_t)(rp * (BLOCK_M * 32) + prow * 32);
+                            for (int c = 0; c < 16; ++c)
+                                m[c] = (((f[2 * c] + f[2 * c + 1]) + f[32 + 2 * c]) + f[32 + 2 * c + 1]) * 0.25f;
 #pragma unroll
-                        for (int ch = 0; ch < 2; ++ch) {
-                            const float* s = l1r + ch * 8;
-                            st_shared_v4(rowaddr + ((ch ^ sw1) << 4), pack_bf16(s[0], s[1]), pack_bf16(s[2], s[3]),
-                                         pack_bf16(s[4], s[5]), pack_bf16(s[6], s[7]));
+                            for (int p = 0; p < 2; ++p) {
+                                const float* s = m + p * 8;
+                                st_shared_v4(wb + ((p ^ wsw_b) << 4), pack_bf16(s[0], s[1]), pack_bf16(s[2], s[3]),
+                                             pack_bf16(s[4], s[5]), pack_bf16(s[6], s[7]));
+                            }
                         }
                     }
-                    if (rp & 1) {
-                        float* l2r = l2[rp >> 1];
+                    __syncwarp();
+                    // ---- stage -> global, 16-byte pieces, 64-byte segments per (query, image row)
+                    const int xh = k / ypairs, yp = k - xh * ypairs;
+                    const int x0 = (tx * P.XH + xh) * 32, y0 = ty * P.PH + 2 * yp;
+                    if (!(PROF && (dbg & 1))) {
+                        const int y = y0 + (ra_p >> 2), x = x0 + (ra_p & 3) * 8;
+                        // pieces are always written whole and the row padding (w..pitch) is written too: TMA
+                        // zero-fills targets outside the image, so the padding receives zeros (finite values --
+                        // the lookup kernel relies on that) and no 32-byte sector is left partially written
+                        // (partial sectors measured a 2x slowdown of the whole kernel at w = 156)
+                        const bool in_img = y < P.la.h && x < P.la.pitch;
+                        const long long off_yx = (long long)y * P.la.pitch + x;
 #pragma unroll
-                        for (int c = 0; c < 8; ++c)
-                            l2r[c] = (((l1[0][2 * c] + l1[0][2 * c + 1]) + l1[1][2 * c]) + l1[1][2 * c + 1]) * 0.25f;
-                        if (P.levels > 2 && !(PROF && (dbg & 16))) {
-                            const uint32_t a2 = st2 + (uint32_t)((rp >> 1) * (BLOCK_M * 16) + prow * 16);
-                            st_shared_v4(a2, pack_bf16(l2r[0], l2r[1]), pack_bf16(l2r[2], l2r[3]),
-                                         pack_bf16(l2r[4], l2r[5]), pack_bf16(l2r[6], l2r[7]));
+                        for (int j = 0; j < 8; ++j) {
+                            const int r = j * 4 + ra_q;
+                            const uint4 val = ld_shared_v4(stg_a + (uint32_t)r * 128u + (uint32_t)((ra_p ^ (r & 7)) << 4));
+                            if (in_img && qrow0 + r < P.Nq) {
+                                st_global_v4(P.la.base + (qglob0 + r) * P.la.q_stride + off_yx, val);
+                            }
                         }
                     }
-                }
-                // accumulator stage drained: hand it back to the MMA warp (leader CTA's barrier)
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                    if (CG == 2) mbar_arrive_cluster(bar_t_empty + 8 * acc, 0);
-                    else mbar_arrive_local(bar_t_empty + 8 * acc);
-                }
-                // level 3: one 8x8 block mean per 8 columns -> 4 values, stored directly
-                if (P.levels > 3 && !(PROF && (dbg & 8))) {
-                    float l3[4];
+                    if (P.has_b && !(PROF && (dbg & 2))) {
+                        const int y = y0 >> 1, x = (x0 >> 1) + rb_p * 8;
+                        const bool in_img = y < P.lb.h && x < P.lb.pitch;
+                        const long long off_yx = (long long)y * P.lb.pitch + x;
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        l3[c] = (((l2[0][2 * c] + l2[0][2 * c + 1]) + l2[1][2 * c]) + l2[1][2 * c + 1]) * 0.25f;
-                    const int p = row0 + prow;
-                    const int x3 = tx * 4, y3 = ty;
-                    if (p < P.N && y3 < P.l3_h) {
-                        __nv_bfloat16* dst = P.l3_base + ((long long)ic.b * P.N + p) * P.l3_qs + (long long)y3 * P.l3_pitch + x3;
-                        if (x3 + 3 < P.l3_w) {
-                            *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(l3[0], l3[1]), pack_bf16(l3[2], l3[3]));
-                        } else {
-#pragma unroll
-                            for (int c = 0; c < 4; ++c)
-                                if (x3 + c < P.l3_w) dst[c] = __float2bfloat16_rn(l3[c]);
+                        for (int j = 0; j < 2; ++j) {
+                            const int r = j * 16 + rb_q;
+                            const uint4 val = ld_shared_v4(stg_b + (uint32_t)r * 32u + (uint32_t)((rb_p ^ ((r >> 2) & 1)) << 4));
+                            if (in_img && qrow0 + r < P.Nq) {
+                                st_global_v4(P.lb.base + (qglob0 + r) * P.lb.q_stride + off_yx, val);
+                            }
                         }
                     }
-                }
-                fence_proxy_async_smem();                  // generic-proxy smem writes -> visible to TMA
-                epi_bar_sync();
-                if (store_thread) {
-                    if (row0 < P.N) {
-                        if (!(PROF && (dbg & 1))) tma_store_4d(&map_l0, st0, tx * PATCH_W, row0, ty * PATCH_H, ic.b);
-                        if (P.levels > 1 && tx * 16 < (P.w >> 1) && ty * 4 < (P.h >> 1) && !(PROF && (dbg & 2)))
-                            tma_store_4d(&map_l1, st1, tx * 16, row0, ty * 4, ic.b);
-                        if (P.levels > 2 && tx * 8 < (P.w >> 2) && ty * 2 < (P.h >> 2) && !(PROF && (dbg & 4)))
-                            tma_store_4d(&map_l2, st2, tx * 8, row0, ty * 2, ic.b);
-                    }
-                    tma_store_commit();
+                    __syncwarp();      // the stage is rewritten by the next chunk
                 }
                 if (++acc == 2) { acc = 0; tphase ^= 1; }
             }
         }
-        if (store_thread) tma_store_wait_all();
-        if (PROF && P.prof && store_thread) {
+        if (PROF && P.prof && warp == 2 && lane == 0) {
             unsigned long long* o = P.prof + (size_t)blockIdx.x * 16;
-            o[5] = pw0; o[6] = pw1; o[7] = ptiles; o[8] = (unsigned long long)(clock64() - t_start);
+            o[5] = pw0; o[6] = 0; o[7] = ptiles; o[8] = (unsigned long long)(clock64() - t_start);
         }
-        __syncwarp();
     }
 
     // teardown: nobody may leave (or free TMEM) while a peer can still signal / read this CTA
@@ -543,7 +564,7 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
     return fn;
 }
 
-bool encode_map(CUtensorMap* m, void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+bool encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                 const uint32_t* box, CUtensorMapSwizzle swz) {
     PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode();
     if (!enc) return false;
@@ -552,24 +573,24 @@ bool encode_map(CUtensorMap* m, void* base, int rank, const uint64_t* dims, cons
     cuuint32_t bx[5];
     for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; }
     for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, gdim, gstr, bx, estr,
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
 
 template <int CG, bool PROF>
-int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& m0, const CUtensorMap& m1,
-                const CUtensorMap& m2, const GemmParams& P, int grid, cudaStream_t st) {
+int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& P, int grid, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        OFB_CUDA(cudaFuncSetAttribute(corr_pyramid_kernel<CG, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
+        OFB_CUDA(cudaFuncSetAttribute(corr_pyramid_kernel<CG, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      Ring<CG>::SMEM_ALLOC));
         configured = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = SMEM_ALLOC;
+    cfg.dynamicSmemBytes = Ring<CG>::SMEM_ALLOC;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -578,37 +599,29 @@ int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    OFB_CUDA(cudaLaunchKernelEx(&cfg, corr_pyramid_kernel<CG, PROF>, ma, mb, m0, m1, m2, P));
+    OFB_CUDA(cudaLaunchKernelEx(&cfg, corr_pyramid_kernel<CG, PROF>, ma, mb, P));
     OFB_LAUNCH_CHECK();
     return OFB_OK;
 }
 
-}  // namespace
-
-static int corr_pyramid_impl(const void* f1_km, const void* f2_km, const ofb_pyramid* pyr, int B, int C, int h, int w,
-                             float scale, int cta_group, unsigned long long* prof, void* stream) {
-    if (!f1_km || !f2_km || !pyr || B < 0 || C <= 0 || h <= 0 || w <= 0) return OFB_EINVAL;
-    if (cta_group < 0 || cta_group > 2) return OFB_EINVAL;
-    if (pyr->levels < 1 || pyr->levels > OFB_MAX_LEVELS) return OFB_EINVAL;
-    if (pyr->dtype != OFB_DTYPE_BF16) return OFB_EUNSUPPORTED;          // fp32 pyramids: ofb_corr_pyramid_simt_f32
-    if (C % BLOCK_K != 0 || C > MAX_KB * BLOCK_K) return OFB_EUNSUPPORTED;
-    if (B == 0) return OFB_OK;
-    if ((reinterpret_cast<uintptr_t>(f1_km) | reinterpret_cast<uintptr_t>(f2_km)) & 15) return OFB_EALIGN;
-    const int N = h * w;
-    for (int l = 0; l < pyr->levels; ++l) {
-        if (!pyr->base[l] || pyr->lvl_h[l] != (h >> l) || pyr->lvl_w[l] != (w >> l)) return OFB_EINVAL;
-        if (pyr->lvl_h[l] <= 0 || pyr->lvl_w[l] <= 0 || pyr->row_pitch[l] < pyr->lvl_w[l]) return OFB_EINVAL;
-        // TMA global strides are multiples of 16 bytes
-        if ((pyr->row_pitch[l] & 7) || (pyr->q_stride[l] & 7) || (reinterpret_cast<uintptr_t>(pyr->base[l]) & 15))
-            return OFB_EALIGN;
-        if (pyr->q_stride[l] < (int64_t)pyr->row_pitch[l] * pyr->lvl_h[l]) return OFB_EINVAL;
-    }
-    const int cg = cta_group == 0 ? 2 : cta_group;
-
+// One GEMM run: queries (B, Nq, C) x targets (B, th*tw, C) -> level la_idx (th x tw per query) and, when
+// lb_idx >= 0, its 2x2 mean.
+int run_gemm(const void* f1_km, const void* f2_km, const ofb_pyramid* pyr, int la_idx, int lb_idx, int B, int C, int Nq,
+             int th, int tw, float scale, int cg, unsigned long long* prof, int prof_slot, cudaStream_t st) {
     GemmParams P = {};
-    P.B = B; P.C = C; P.h = h; P.w = w; P.N = N; P.levels = pyr->levels; P.kb = C / BLOCK_K; P.scale = scale;
-    P.ntx = (w + PATCH_W - 1) / PATCH_W; P.nty = (h + PATCH_H - 1) / PATCH_H; P.ntiles = P.ntx * P.nty;
-    P.mblk = (N + BLOCK_M * cg - 1) / (BLOCK_M * cg);
+    P.B = B; P.C = C; P.kb = C / BLOCK_K; P.Nq = Nq; P.th = th; P.tw = tw;
+    P.scale = scale; P.apply_scale = (scale != 1.0f) ? 1 : 0;
+    // tile shape: 32x8, 64x4 or 128x2 targets -- the one that covers the image with the fewest tiles
+    long long best = -1;
+    for (int xh = 1; xh <= 4; xh *= 2) {
+        const int ph = 8 / xh;
+        const long long tiles = (long long)((tw + 32 * xh - 1) / (32 * xh)) * ((th + ph - 1) / ph);
+        if (best < 0 || tiles <= best) { best = tiles; P.XH = xh; P.PH = ph; }   // ties: the widest tile (longer runs per row)
+    }
+    P.ntx = (tw + 32 * P.XH - 1) / (32 * P.XH); P.nty = (th + P.PH - 1) / P.PH; P.ntiles = P.ntx * P.nty;
+    if (cg == 2) { P.nbox = P.XH >= 2 ? P.XH / 2 : 1; P.box_rows = P.XH == 1 ? P.PH / 2 : P.PH; }
+    else { P.nbox = P.XH; P.box_rows = P.PH; }
+    P.mblk = (Nq + BLOCK_M * cg - 1) / (BLOCK_M * cg);
     const int workers = ofb_num_sms() / cg;
     // split the target tiles of one (batch, query block) into chunks so the last wave is not mostly idle:
     // pick the chunk count (<= 8) that minimises ceil(items / workers) * tiles_per_item
@@ -627,59 +640,86 @@ static int corr_pyramid_impl(const void* f1_km, const void* f2_km, const ofb_pyr
     const long long n_items = (long long)B * P.mblk * P.n_chunks;
     if (n_items > 0x7fffffffLL) return OFB_EUNSUPPORTED;
     P.n_items = (int)n_items;
-    if (pyr->levels > 3) {
-        P.l3_base = reinterpret_cast<__nv_bfloat16*>(pyr->base[3]);
-        P.l3_qs = pyr->q_stride[3]; P.l3_pitch = pyr->row_pitch[3]; P.l3_h = pyr->lvl_h[3]; P.l3_w = pyr->lvl_w[3];
+    P.la.base = reinterpret_cast<__nv_bfloat16*>(pyr->base[la_idx]);
+    P.la.q_stride = pyr->q_stride[la_idx]; P.la.pitch = pyr->row_pitch[la_idx];
+    P.la.h = pyr->lvl_h[la_idx]; P.la.w = pyr->lvl_w[la_idx];
+    P.has_b = lb_idx >= 0 ? 1 : 0;
+    if (P.has_b) {
+        P.lb.base = reinterpret_cast<__nv_bfloat16*>(pyr->base[lb_idx]);
+        P.lb.q_stride = pyr->q_stride[lb_idx]; P.lb.pitch = pyr->row_pitch[lb_idx];
+        P.lb.h = pyr->lvl_h[lb_idx]; P.lb.w = pyr->lvl_w[lb_idx];
     }
-
-    CUtensorMap ma, mb, ml[3];
-    {
-        const uint64_t dims[3] = {(uint64_t)C, (uint64_t)N, (uint64_t)B};
-        const uint64_t str[2] = {(uint64_t)C * 2, (uint64_t)N * C * 2};
-        const uint32_t box[3] = {BLOCK_K, BLOCK_M, 1};
-        if (!encode_map(&ma, const_cast<void*>(f1_km), 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return OFB_EDRIVER;
-    }
-    {
-        const uint64_t dims[4] = {(uint64_t)C, (uint64_t)w, (uint64_t)h, (uint64_t)B};
-        const uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)w * C * 2, (uint64_t)N * C * 2};
-        const uint32_t box[4] = {BLOCK_K, PATCH_W, (uint32_t)(PATCH_H / cg), 1};
-        if (!encode_map(&mb, const_cast<void*>(f2_km), 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return OFB_EDRIVER;
-    }
-    for (int l = 0; l < 3; ++l) {
-        const int ll = l < pyr->levels ? l : 0;   // unused maps alias level 0 (never stored through)
-        const uint64_t dims[4] = {(uint64_t)pyr->lvl_w[ll], (uint64_t)N, (uint64_t)pyr->lvl_h[ll], (uint64_t)B};
-        const uint64_t str[3] = {(uint64_t)pyr->q_stride[ll] * 2, (uint64_t)pyr->row_pitch[ll] * 2,
-                                 (uint64_t)N * pyr->q_stride[ll] * 2};
-        const uint32_t box[4] = {(uint32_t)(PATCH_W >> ll), BLOCK_M, (uint32_t)(PATCH_H >> ll), 1};
-        const CUtensorMapSwizzle swz = ll == 0 ? CU_TENSOR_MAP_SWIZZLE_64B
-                                     : ll == 1 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
-        if (!encode_map(&ml[l], pyr->base[ll], 4, dims, str, box, swz)) return OFB_EDRIVER;
-    }
-    int grid = workers * cg;
-    if ((long long)grid > n_items * cg) grid = (int)(n_items * cg);
-    cudaStream_t st = (cudaStream_t)stream;
-    P.prof = prof;
+    P.prof = prof ? prof + (size_t)prof_slot * PROF_SLOT : nullptr;
     P.dbg = 0;
     if (prof) {
         const char* e = getenv("OFB_K2_DBG");
         if (e) P.dbg = atoi(e);
     }
-    if (prof) {
-        if (cg == 2) return launch_gemm<2, true>(ma, mb, ml[0], ml[1], ml[2], P, grid, st);
-        return launch_gemm<1, true>(ma, mb, ml[0], ml[1], ml[2], P, grid, st);
+
+    CUtensorMap ma, mb;
+    {
+        const uint64_t dims[3] = {(uint64_t)C, (uint64_t)Nq, (uint64_t)B};
+        const uint64_t str[2] = {(uint64_t)C * 2, (uint64_t)Nq * C * 2};
+        const uint32_t box[3] = {BLOCK_K, BLOCK_M, 1};
+        if (!encode_map(&ma, f1_km, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return OFB_EDRIVER;
     }
-    if (cg == 2) return launch_gemm<2, false>(ma, mb, ml[0], ml[1], ml[2], P, grid, st);
-    return launch_gemm<1, false>(ma, mb, ml[0], ml[1], ml[2], P, grid, st);
+    {
+        const uint64_t dims[4] = {(uint64_t)C, (uint64_t)tw, (uint64_t)th, (uint64_t)B};
+        const uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)tw * C * 2, (uint64_t)th * tw * C * 2};
+        const uint32_t box[4] = {BLOCK_K, 32, (uint32_t)P.box_rows, 1};
+        if (!encode_map(&mb, f2_km, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return OFB_EDRIVER;
+    }
+    int grid = workers * cg;
+    if ((long long)grid > n_items * cg) grid = (int)(n_items * cg);
+    if (prof) {
+        if (cg == 2) return launch_gemm<2, true>(ma, mb, P, grid, st);
+        return launch_gemm<1, true>(ma, mb, P, grid, st);
+    }
+    if (cg == 2) return launch_gemm<2, false>(ma, mb, P, grid, st);
+    return launch_gemm<1, false>(ma, mb, P, grid, st);
 }
 
-OFB_API int ofb_corr_pyramid_bf16(const void* f1_km, const void* f2_km, const ofb_pyramid* pyr, int B, int C, int h,
-                                  int w, float scale, int cta_group, void* stream) {
-    return corr_pyramid_impl(f1_km, f2_km, pyr, B, C, h, w, scale, cta_group, nullptr, stream);
+int corr_pyramid_impl(const void* f1_km, const void* f2_km, const void* f2q_km, const ofb_pyramid* pyr, int B, int C, int h,
+                      int w, float scale, int cta_group, unsigned long long* prof, void* stream) {
+    if (!f1_km || !f2_km || !pyr || B < 0 || C <= 0 || h <= 0 || w <= 0) return OFB_EINVAL;
+    if (cta_group < 0 || cta_group > 2) return OFB_EINVAL;
+    if (pyr->levels < 1 || pyr->levels > OFB_MAX_LEVELS) return OFB_EINVAL;
+    if (pyr->dtype != OFB_DTYPE_BF16) return OFB_EUNSUPPORTED;          // fp32 pyramids: ofb_corr_pyramid_simt_f32
+    if (C % BLOCK_K != 0 || C > MAX_KB * BLOCK_K) return OFB_EUNSUPPORTED;
+    if (pyr->levels > 2 && !f2q_km) return OFB_EINVAL;                  // levels 2, 3 come from the 4x4-averaged fmap2
+    if (B == 0) return OFB_OK;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(f1_km) | reinterpret_cast<uintptr_t>(f2_km) |
+                         reinterpret_cast<uintptr_t>(f2q_km);
+    if (al & 15) return OFB_EALIGN;
+    for (int l = 0; l < pyr->levels; ++l) {
+        if (!pyr->base[l] || pyr->lvl_h[l] != (h >> l) || pyr->lvl_w[l] != (w >> l)) return OFB_EINVAL;
+        if (pyr->lvl_h[l] <= 0 || pyr->lvl_w[l] <= 0 || pyr->row_pitch[l] < pyr->lvl_w[l]) return OFB_EINVAL;
+        // 16-byte store pieces: rows and query slices start on 8-element boundaries
+        if ((pyr->row_pitch[l] & 7) || (pyr->q_stride[l] & 7) || (reinterpret_cast<uintptr_t>(pyr->base[l]) & 15))
+            return OFB_EALIGN;
+        if (pyr->q_stride[l] < (int64_t)pyr->row_pitch[l] * pyr->lvl_h[l]) return OFB_EINVAL;
+    }
+    // auto: one CTA per tile -- measured faster than the CTA pair on every BASELINE shape once the
+    // kernel became HBM-write-bound (profiles/r01_k2_findings.md); the pair halves operand traffic but
+    // couples two epilogues through one accumulator barrier
+    const int cg = cta_group == 0 ? 1 : cta_group;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int rc = run_gemm(f1_km, f2_km, pyr, 0, pyr->levels > 1 ? 1 : -1, B, C, h * w, h, w, scale, cg, prof, 0, st);
+    if (rc != OFB_OK || pyr->levels <= 2) return rc;
+    return run_gemm(f1_km, f2q_km, pyr, 2, pyr->levels > 3 ? 3 : -1, B, C, h * w, h >> 2, w >> 2, scale, cg, prof, 1, st);
 }
 
-OFB_API int ofb_corr_pyramid_bf16_profile(const void* f1_km, const void* f2_km, const ofb_pyramid* pyr, int B, int C,
-                                          int h, int w, float scale, int cta_group, uint64_t* prof_dev, void* stream) {
+}  // namespace
+
+OFB_API int ofb_corr_pyramid_bf16(const void* f1_km, const void* f2_km, const void* f2q_km, const ofb_pyramid* pyr, int B,
+                                  int C, int h, int w, float scale, int cta_group, void* stream) {
+    return corr_pyramid_impl(f1_km, f2_km, f2q_km, pyr, B, C, h, w, scale, cta_group, nullptr, stream);
+}
+
+OFB_API int ofb_corr_pyramid_bf16_profile(const void* f1_km, const void* f2_km, const void* f2q_km, const ofb_pyramid* pyr,
+                                          int B, int C, int h, int w, float scale, int cta_group, uint64_t* prof_dev,
+                                          void* stream) {
     if (!prof_dev) return OFB_EINVAL;
-    return corr_pyramid_impl(f1_km, f2_km, pyr, B, C, h, w, scale, cta_group,
+    return corr_pyramid_impl(f1_km, f2_km, f2q_km, pyr, B, C, h, w, scale, cta_group,
                              reinterpret_cast<unsigned long long*>(prof_dev), stream);
 }

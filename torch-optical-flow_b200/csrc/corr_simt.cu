@@ -1,9 +1,11 @@
 // corr_simt.cu -- operand preparation for K2 and a CUDA-core correlation-pyramid builder.
 //
-//  * ofb_corr_prep_bf16: fmap (B,C,h*w) fp32 NCHW -> (B,h*w,C) bf16, K-major.  Replaces the
-//    .view / .transpose(1,2) in CorrBlock.corr (reference methods/raft/model/corr.py:82-85) and
-//    is the only extra pass the tensor-core path needs (reads 4 B, writes 2 B per element;
-//    0.17 GB at the Sintel configuration against 2.1 GB of pyramid).
+//  * ofb_corr_prep_bf16: fmap (B,C,h,w) fp32 NCHW -> (B,(h/pool)*(w/pool),C) bf16, K-major, times
+//    `scale`, optionally averaged over complete pool x pool blocks.  Replaces the .view /
+//    .transpose(1,2) in CorrBlock.corr (reference methods/raft/model/corr.py:82-85), folds the
+//    1/sqrt(C) of corr.py:87 into fmap1, and -- pool = 4 on fmap2 -- feeds the run that produces
+//    pyramid levels 2 and 3 (avg_pool2d is linear: corr.py:52-54).  The only extra passes the
+//    tensor-core path needs (0.2 GB at the Sintel configuration against 2.1 GB of pyramid).
 //  * ofb_pyramid_layout: strides of the pyramid buffers (see include/ofb200.h).
 //  * ofb_corr_pyramid_simt_f32: fp32 CUDA-core GEMM + successive 2x2 pooling -- the reference's
 //    own op order (corr.py:44-54,79-87).  Not the fast path: tests use it as an on-device
@@ -16,23 +18,41 @@ namespace {
 constexpr int TP = 32;  // pixels per tile
 constexpr int TC = 64;  // channels per tile
 
+template <int POOL>
 __global__ void __launch_bounds__(256) prep_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int C,
-                                                   int HW) {
+                                                   int h, int w, float scale) {
+    // output pixel p = (yo, xo) of the (h/POOL) x (w/POOL) image = mean of a complete POOL x POOL block
     __shared__ float tile[TC][TP + 1];
+    const int ho = h / POOL, wo = w / POOL, HWo = ho * wo, HW = h * w;
     const int b = blockIdx.z, p0 = blockIdx.x * TP, c0 = blockIdx.y * TC;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // read: 64 channel rows x 32 pixels, each row segment one 128-byte line
+    // read: 64 channel rows x 32 pixels (POOL = 1: each row segment one 128-byte line)
+    const int p = p0 + lane;
+    const int yo = p / wo, xo = p - yo * wo;
     for (int c = warp; c < TC; c += 8) {
-        const int cc = c0 + c, p = p0 + lane;
-        tile[c][lane] = (cc < C && p < HW) ? __ldg(in + ((size_t)b * C + cc) * HW + p) : 0.0f;
+        const int cc = c0 + c;
+        float v = 0.0f;
+        if (cc < C && p < HWo) {
+            const float* src = in + ((size_t)b * C + cc) * HW + (size_t)(yo * POOL) * w + xo * POOL;
+            if (POOL == 1) {
+                v = __ldg(src);
+            } else {
+#pragma unroll
+                for (int dy = 0; dy < POOL; ++dy)
+#pragma unroll
+                    for (int dx = 0; dx < POOL; ++dx) v += __ldg(src + dy * w + dx);
+                v *= 1.0f / (float)(POOL * POOL);
+            }
+        }
+        tile[c][lane] = v * scale;
     }
     __syncthreads();
     // write: per pixel 64 channels = 128 bytes, one bf16x2 per lane
-    for (int p = warp; p < TP; p += 8) {
-        const int pp = p0 + p, cc = c0 + 2 * lane;
-        if (pp < HW && cc < C) {
-            __nv_bfloat162 v = __floats2bfloat162_rn(tile[2 * lane][p], tile[2 * lane + 1][p]);
-            *reinterpret_cast<__nv_bfloat162*>(out + ((size_t)b * HW + pp) * C + cc) = v;
+    for (int q = warp; q < TP; q += 8) {
+        const int pp = p0 + q, cc = c0 + 2 * lane;
+        if (pp < HWo && cc < C) {
+            __nv_bfloat162 v = __floats2bfloat162_rn(tile[2 * lane][q], tile[2 * lane + 1][q]);
+            *reinterpret_cast<__nv_bfloat162*>(out + ((size_t)b * HWo + pp) * C + cc) = v;
         }
     }
 }
@@ -126,14 +146,19 @@ int build_simt(const float* f1, const float* f2, const ofb_pyramid* pyr, int B, 
 
 }  // namespace
 
-OFB_API int ofb_corr_prep_bf16(const float* fmap_nchw, void* out_km_bf16, int B, int C, int HW, void* stream) {
-    if (!fmap_nchw || !out_km_bf16 || B < 0 || C <= 0 || HW <= 0) return OFB_EINVAL;
+OFB_API int ofb_corr_prep_bf16(const float* fmap_nchw, void* out_km_bf16, int B, int C, int h, int w, int pool,
+                               float scale, void* stream) {
+    if (!fmap_nchw || !out_km_bf16 || B < 0 || C <= 0 || h <= 0 || w <= 0) return OFB_EINVAL;
+    if (pool != 1 && pool != 4) return OFB_EINVAL;
     if (C & 1) return OFB_EUNSUPPORTED;
     if (reinterpret_cast<uintptr_t>(out_km_bf16) & 3) return OFB_EALIGN;
-    if (B == 0) return OFB_OK;
+    const int HWo = (h / pool) * (w / pool);
+    if (B == 0 || HWo == 0) return OFB_OK;
     if (B > 65535) return OFB_EUNSUPPORTED;
-    dim3 grid((HW + TP - 1) / TP, (C + TC - 1) / TC, B);
-    prep_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(fmap_nchw, reinterpret_cast<__nv_bfloat16*>(out_km_bf16), C, HW);
+    dim3 grid((HWo + TP - 1) / TP, (C + TC - 1) / TC, B);
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(out_km_bf16);
+    if (pool == 1) prep_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(fmap_nchw, out, C, h, w, scale);
+    else prep_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(fmap_nchw, out, C, h, w, scale);
     OFB_LAUNCH_CHECK();
     return OFB_OK;
 }
@@ -149,7 +174,7 @@ OFB_API int ofb_pyramid_layout(int h, int w, int levels, int padded, ofb_pyramid
     for (int l = 0; l < levels; ++l) {
         const int hl = h >> l, wl = w >> l;
         if (hl <= 0 || wl <= 0) return OFB_EINVAL;   // F.avg_pool2d raises "Output size is too small" (corr.py:53)
-        const int pitch = padded ? ((wl + 7) & ~7) : wl;
+        const int pitch = padded ? ((wl + 15) & ~15) : wl;   // rows start on 32-byte sectors (bf16)
         pyr->lvl_h[l] = hl; pyr->lvl_w[l] = wl; pyr->row_pitch[l] = pitch;
         pyr->q_stride[l] = (int64_t)pitch * hl;
         if (elems) elems[l] = pyr->q_stride[l];      // per query; caller multiplies by B*h*w

@@ -23,6 +23,9 @@
 //      its cell from the owning lanes with warp shuffles.
 // Results are staged in a [channel][query] shared tile so the global writes are 128-byte rows.
 // HBM roofline per query and iteration: L*(2r+2)^2*esize + 8 read, 4*L*(2r+1)^2 written.
+#include <climits>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -181,6 +184,183 @@ __global__ void __launch_bounds__(NW * 32) lookup_kernel(const LookupParams P, c
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Register-tile lookup for bf16 pyramids (the product path).
+//
+// thread = (query, level): lane <-> query (coordinates in, channel rows out are 128-byte coalesced),
+// warp <-> pyramid level.  Each thread
+//   1. evaluates its 2*(2R+1) tap coordinates with the bit-exact sequence above;
+//   2. anchors an 11 x 11 element window at (xs, ys) = min over taps of (floor index - tap number).
+//      Within the guarded coordinate range every tap's floor index is tap + anchor + {0, 1} (the fp32
+//      round trip can move a tap sitting on an integer to the pixel below), so tap i reads window
+//      columns i .. i+2 through a 3-tap filter (w0, w1, 0) or (0, w0, w1) -- the same products as
+//      the reference's 2-tap form plus exact zeros;
+//   3. streams the window row by row: 16-byte aligned chunk loads (2.25 per row on average),
+//      realigned in registers with two select stages (word shift) and a funnel shift (half-word),
+//      horizontal filter -> 9 values, vertical filter accumulated into three live output rows;
+//   4. writes each finished output row straight to its 9 channels.
+// No shared memory, no shuffles, ~56 warp instructions per (query, level) against ~230 before.
+// Contract with the builder: elements between w_l and the row pitch hold FINITE values (the tcgen05
+// builder writes zeros there); they are multiplied by zero weights.
+template <int R>
+struct TapSet {
+    static constexpr int D = 2 * R + 1;
+    float w0[D], w1[D];
+    int anchor;          // min over taps of (floor index - tap number); tap t reads anchor + t + d[t]
+    unsigned dmask;      // bit t = d[t]
+    unsigned vmask;      // bit t = utils.py:77 predicate
+    bool dead;           // some tap outside the guarded range: every in-range tap is outside the image
+};
+
+template <int R>
+__device__ __forceinline__ TapSet<R> make_taps(float center, int size, int32_t* idx_dst) {
+    constexpr int D = 2 * R + 1;
+    TapSet<R> ts;
+    int i0[D];
+    ts.dead = false;
+    ts.vmask = 0;
+    const float sm1 = (float)(size - 1);
+    int anchor = INT_MAX;
+#pragma unroll
+    for (int t = 0; t < D; ++t) {
+        const float pos = __fadd_rn(center, (float)(t - R));
+        const float g = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, pos), sm1), 1.0f);
+        const float ic = __fmul_rn(__fmul_rn(__fadd_rn(g, 1.0f), 0.5f), sm1);   // x / 2 == x * 0.5 exactly
+        const float fl = floorf(ic);
+        ts.w1[t] = __fsub_rn(ic, fl);
+        ts.w0[t] = __fsub_rn(__fadd_rn(fl, 1.0f), ic);
+        // guard for the int conversion; a tap outside it implies the whole window is outside the image
+        // (level sizes are <= 65536), and inside it fp32 resolves the coordinate to better than 1/64
+        const bool ok = fl >= -32768.0f && fl <= 70000.0f;
+        ts.dead |= !ok;
+        i0[t] = ok ? (int)fl : 0;
+        if (idx_dst) idx_dst[t] = (int32_t)fl;
+        ts.vmask |= ((g > -1.0f) && (g < 1.0f)) ? (1u << t) : 0u;
+        anchor = min(anchor, i0[t] - t);
+    }
+    ts.anchor = anchor;
+    ts.dmask = 0;
+#pragma unroll
+    for (int t = 0; t < D; ++t) {
+        const int d = i0[t] - t - anchor;           // 0 or 1 unless dead
+        ts.dmask |= (d != 0) ? (1u << t) : 0u;
+        ts.dead |= (d > 1);
+    }
+    return ts;
+}
+
+template <int R>
+__global__ void __launch_bounds__(128) lookup_tile_kernel(const LookupParams P, const float* __restrict__ coords,
+                                                           float* __restrict__ out, int32_t* __restrict__ idx_out,
+                                                           uint8_t* __restrict__ valid_out) {
+    constexpr int D = 2 * R + 1, DD = D * D, WIN = D + 2;       // window rows / columns
+    constexpr int NW = (WIN + 1) / 2;                           // packed words per realigned row (6 for R = 4)
+    const int l = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long HW = (long long)P.h * P.w, Q = (long long)P.B * HW;
+    const long long q = (long long)blockIdx.x * 32 + lane;
+    if (q >= Q) return;
+    const long long b = q / HW, p = q - b * HW;
+    const int Wl = P.lw[l], Hl = P.lh[l], pitch = P.pitch[l];
+    const float inv = 1.0f / (float)(1 << l);                   // exact power of two
+    const float cx = __fmul_rn(__ldg(coords + (b * 2 + 0) * HW + p), inv);
+    const float cy = __fmul_rn(__ldg(coords + (b * 2 + 1) * HW + p), inv);
+
+    int32_t* idx_q = idx_out ? idx_out + ((q * P.levels + l) * 2) * D : nullptr;
+    const TapSet<R> tx = make_taps<R>(cx, Wl, idx_q);
+    const TapSet<R> ty = make_taps<R>(cy, Hl, idx_q ? idx_q + D : nullptr);
+    const bool dead = tx.dead || ty.dead;
+    if (valid_out) {
+        uint8_t* vq = valid_out + (q * P.levels + l) * DD;
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j < D; ++j) vq[i * D + j] = (uint8_t)(((tx.vmask >> i) & 1u) & ((ty.vmask >> j) & 1u));
+    }
+
+    // horizontal 3-tap filters; a column outside [0, w_l) gets weight zero (zeros padding)
+    const int xs = dead ? 0 : tx.anchor, ys = dead ? 0 : ty.anchor;
+    float fw[D][3];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        const bool d = (tx.dmask >> i) & 1u;
+        float a0 = d ? 0.0f : tx.w0[i], a1 = d ? tx.w0[i] : tx.w1[i], a2 = d ? tx.w1[i] : 0.0f;
+        const int c0 = xs + i;
+        if (dead || c0 < 0 || c0 >= Wl) a0 = 0.0f;
+        if (dead || c0 + 1 < 0 || c0 + 1 >= Wl) a1 = 0.0f;
+        if (dead || c0 + 2 < 0 || c0 + 2 >= Wl) a2 = 0.0f;
+        fw[i][0] = a0; fw[i][1] = a1; fw[i][2] = a2;
+    }
+
+    // chunk geometry: 8-element (16-byte) aligned chunks covering columns xs .. xs + WIN - 1
+    const int xa = xs & ~7, s = xs - xa;                        // s in 0..7
+    const unsigned q1 = (unsigned)(s >> 1) & 1u, q2 = (unsigned)(s >> 2) & 1u, hs = (unsigned)(s & 1) * 16u;
+    const bool ck0 = xa >= 0 && xa + 8 <= pitch;
+    const bool ck1 = xa + 8 >= 0 && xa + 16 <= pitch;
+    const bool ck2 = (s + WIN > 16) && xa + 16 >= 0 && xa + 24 <= pitch;
+    const __nv_bfloat16* slice = reinterpret_cast<const __nv_bfloat16*>(P.base[l]) + q * P.q_stride[l];
+    float* outp = out + (b * (long long)(P.levels * DD) + (long long)l * DD) * HW + p;
+
+    float acc[3][D];                                            // output rows j = r, r-1, r-2 in flight
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int i = 0; i < D; ++i) acc[k][i] = 0.0f;
+
+    uint4 c0v, c1v;
+    uint2 c2v;
+    auto load_row = [&](int r) {
+        const int y = ys + r;
+        const bool rok = !dead && y >= 0 && y < Hl;
+        const __nv_bfloat16* row = slice + (long long)y * pitch + xa;
+        c0v = make_uint4(0, 0, 0, 0); c1v = make_uint4(0, 0, 0, 0); c2v = make_uint2(0, 0);
+        if (rok && ck0) c0v = __ldg(reinterpret_cast<const uint4*>(row));
+        if (rok && ck1) c1v = __ldg(reinterpret_cast<const uint4*>(row + 8));
+        if (rok && ck2) c2v = __ldg(reinterpret_cast<const uint2*>(row + 16));
+    };
+    load_row(0);
+#pragma unroll
+    for (int r = 0; r < WIN; ++r) {
+        const uint32_t w[10] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w, c2v.x, c2v.y};
+        if (r + 1 < WIN) load_row(r + 1);                       // prefetch the next row while this one is filtered
+        // ---- realign: drop s leading elements (word shifts by 1 and 2, then a half-word funnel shift)
+        uint32_t t1[9], t2[NW + 1], v[NW];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) t1[k] = q1 ? w[k + 1] : w[k];
+#pragma unroll
+        for (int k = 0; k <= NW; ++k) t2[k] = q2 ? t1[k + 2] : t1[k];
+#pragma unroll
+        for (int k = 0; k < NW; ++k) v[k] = __funnelshift_r(t2[k], t2[k + 1], hs);
+        float px[WIN];
+#pragma unroll
+        for (int e = 0; e < WIN; ++e)
+            px[e] = __uint_as_float((e & 1) ? (v[e >> 1] & 0xffff0000u) : (v[e >> 1] << 16));
+        // ---- horizontal filter
+        float hrow[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+            hrow[i] = __fmaf_rn(fw[i][2], px[i + 2], __fmaf_rn(fw[i][1], px[i + 1], __fmul_rn(fw[i][0], px[i])));
+        // ---- vertical filter: window row r feeds output rows j = r (tap 0), r-1 (tap 1), r-2 (tap 2)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int j = r - k;
+            if (j < 0 || j >= D) continue;
+            const bool d = (ty.dmask >> j) & 1u;
+            const float vw = k == 0 ? (d ? 0.0f : ty.w0[j]) : k == 1 ? (d ? ty.w0[j] : ty.w1[j]) : (d ? ty.w1[j] : 0.0f);
+#pragma unroll
+            for (int i = 0; i < D; ++i) acc[(j % 3)][i] = __fmaf_rn(vw, hrow[i], acc[(j % 3)][i]);
+        }
+        // ---- output row j = r - 2 is complete: channel = l*DD + i*D + j  (i moves x: corr.py:64-70)
+        if (r >= 2) {
+            const int j = r - 2;
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                outp[(long long)(i * D + j) * HW] = acc[j % 3][i];
+                acc[j % 3][i] = 0.0f;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) bilinear_sampler_kernel(const float* __restrict__ img,
                                                                const float* __restrict__ coords,
                                                                float* __restrict__ out, float* __restrict__ mask, int N,
@@ -243,6 +423,17 @@ OFB_API int ofb_corr_lookup(const ofb_pyramid* pyr, const float* coords, float* 
     const long long blocks = (Q + QT - 1) / QT;
     if (blocks > 0x7fffffffLL) return OFB_EUNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
+    // product path: bf16 pyramid with padded rows (pitch multiple of 8, 16-byte aligned slices)
+    bool tile_ok = pyr->dtype == OFB_DTYPE_BF16 && (radius == 4 || radius == 3) && !getenv("OFB_LOOKUP_V1");
+    for (int l = 0; l < pyr->levels && tile_ok; ++l)
+        tile_ok = (P.pitch[l] % 8 == 0) && (P.q_stride[l] % 8 == 0) && ((reinterpret_cast<uintptr_t>(P.base[l]) & 15) == 0);
+    if (tile_ok) {
+        const int threads = 32 * pyr->levels;
+        if (radius == 4) lookup_tile_kernel<4><<<(int)blocks, threads, 0, st>>>(P, coords, out, idx_or_null, valid_or_null);
+        else lookup_tile_kernel<3><<<(int)blocks, threads, 0, st>>>(P, coords, out, idx_or_null, valid_or_null);
+        OFB_LAUNCH_CHECK();
+        return OFB_OK;
+    }
     if (pyr->dtype == OFB_DTYPE_BF16) {
         OFB_CUDA(cudaFuncSetAttribute(lookup_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         lookup_kernel<__nv_bfloat16><<<(int)blocks, NW * 32, smem, st>>>(P, coords, out, idx_or_null, valid_or_null);

@@ -23,6 +23,24 @@ def _default_pyramid_dtype() -> torch.dtype:
     return torch.float32 if os.environ.get("OFB200_PYRAMID_DTYPE", "bf16").lower() in ("fp32", "f32", "float32") else torch.bfloat16
 
 
+def prepare_operands(fmap1: Tensor, fmap2: Tensor, num_levels: int):
+    """K-major bf16 operands of the tcgen05 builder: fmap1 * 1/sqrt(C), fmap2, and (for pyramids with
+    more than two levels) fmap2 averaged over complete 4x4 blocks.  fp32 (B, C, h, w) CUDA inputs."""
+    b, c, h, w = fmap1.shape
+    lib = ofb200.load()
+    st = ofb200.stream_ptr()
+    dev = fmap1.device
+    a_km = torch.empty((b, h * w, c), dtype=torch.bfloat16, device=dev)
+    b_km = torch.empty((b, h * w, c), dtype=torch.bfloat16, device=dev)
+    q_km = torch.empty((b, (h // 4) * (w // 4), c), dtype=torch.bfloat16, device=dev) if num_levels > 2 else None
+    scale = 1.0 / math.sqrt(float(c))
+    ofb200.check(lib.ofb_corr_prep_bf16(ofb200.ptr(fmap1), ofb200.ptr(a_km), b, c, h, w, 1, scale, st), "ofb_corr_prep_bf16")
+    ofb200.check(lib.ofb_corr_prep_bf16(ofb200.ptr(fmap2), ofb200.ptr(b_km), b, c, h, w, 1, 1.0, st), "ofb_corr_prep_bf16")
+    if q_km is not None:
+        ofb200.check(lib.ofb_corr_prep_bf16(ofb200.ptr(fmap2), ofb200.ptr(q_km), b, c, h, w, 4, 1.0, st), "ofb_corr_prep_bf16")
+    return a_km, b_km, q_km
+
+
 class CorrBlock:
     def __init__(
         self,
@@ -74,7 +92,10 @@ class CorrBlock:
         self._buffers = []
         with torch.cuda.device(self._dev):
             for lvl in range(num_levels):
-                buf = torch.empty(b * n * int(pyr.q_stride[lvl]), dtype=pyramid_dtype, device=self._dev)
+                # the tcgen05 builder writes the row padding itself (zeros); the CUDA-core builder does not,
+                # and the lookup kernel requires finite values there
+                alloc = torch.empty if builder == "tcgen05" else torch.zeros
+                buf = alloc(b * n * int(pyr.q_stride[lvl]), dtype=pyramid_dtype, device=self._dev)
                 self._buffers.append(buf)
                 pyr.base[lvl] = buf.data_ptr()
                 qs, pitch = int(pyr.q_stride[lvl]), int(pyr.row_pitch[lvl])
@@ -84,17 +105,14 @@ class CorrBlock:
             self._pyr = pyr
             scale = 1.0 / math.sqrt(float(c))
             if builder == "tcgen05":
-                a_km = torch.empty((b, n, c), dtype=torch.bfloat16, device=self._dev)
-                b_km = torch.empty((b, n, c), dtype=torch.bfloat16, device=self._dev)
-                st = ofb200.stream_ptr()
-                ofb200.check(lib.ofb_corr_prep_bf16(ofb200.ptr(fmap1), ofb200.ptr(a_km), b, c, n, st), "ofb_corr_prep_bf16")
-                ofb200.check(lib.ofb_corr_prep_bf16(ofb200.ptr(fmap2), ofb200.ptr(b_km), b, c, n, st), "ofb_corr_prep_bf16")
-                rc = lib.ofb_corr_pyramid_bf16(ofb200.ptr(a_km), ofb200.ptr(b_km), ctypes.byref(pyr), b, c, h, w,
-                                               scale, int(cta_group), st)
+                ops = prepare_operands(fmap1, fmap2, num_levels)
+                rc = lib.ofb_corr_pyramid_bf16(ofb200.ptr(ops[0]), ofb200.ptr(ops[1]), ofb200.ptr(ops[2]),
+                                               ctypes.byref(pyr), b, c, h, w, 1.0, int(cta_group), ofb200.stream_ptr())
                 ofb200.check(rc, "ofb_corr_pyramid_bf16")
                 # keep the operands alive until the stream has consumed them
-                a_km.record_stream(torch.cuda.current_stream())
-                b_km.record_stream(torch.cuda.current_stream())
+                for t in ops:
+                    if t is not None:
+                        t.record_stream(torch.cuda.current_stream())
             elif builder == "simt":
                 rc = lib.ofb_corr_pyramid_simt_f32(ofb200.ptr(fmap1), ofb200.ptr(fmap2), ctypes.byref(pyr), b, c, h, w,
                                                    scale, ofb200.stream_ptr())

@@ -5,7 +5,7 @@ The pass is the sequence the reference's RAFT.forward drives per pair (reference
 methods/raft/model/raft.py:112-142) followed by the library operators and metric it feeds
 (optical_flow/operator/operator.py:8-33, optical_flow/metrics/epe.py:25-38):
 
-    CorrBlock(fmap1, fmap2)                    K2  prep x2 + tcgen05 pyramid
+    CorrBlock(fmap1, fmap2)                    K2  prep x3 + tcgen05 pyramid x2 (levels 0-1, levels 2-3)
     corr_fn(coords) x iters                    K3  one launch per refinement iteration
     RAFT.upsample_flow(flow_lo, up_mask)       K4b convex 8x upsampling
     warp(frame, normalize(flow_up)) + mask     scale + K1
@@ -74,7 +74,7 @@ def hot_path(batch: Dict[str, Tensor], metric: AverageEndPointError, timers: Opt
              lookup_out: Optional[Tensor] = None, cta_group: int = 0) -> Dict[str, Tensor]:
     """Run the pass on device tensors.  `batch["coords"]` is (iters, B, 2, h, w)."""
     sp = (lambda n, k: timers.span(n, k)) if timers is not None else (lambda n, k: _NoSpan())
-    with sp("corr_pyramid", 3):
+    with sp("corr_pyramid", 5):
         blk = CorrBlock(batch["fmap1"], batch["fmap2"], num_levels=4, radius=4, cta_group=cta_group)
     iters = batch["coords"].shape[0]
     corr = None
@@ -90,7 +90,7 @@ def hot_path(batch: Dict[str, Tensor], metric: AverageEndPointError, timers: Opt
     return {"corr": corr, "flow_up": flow_up, "warped": warped, "mask": vmask}
 
 
-LAUNCHES_PER_PASS = lambda iters: 3 + iters + 1 + 2 + 1  # noqa: E731  (prep x2, pyramid, lookups, upsample, scale, warp, epe)
+LAUNCHES_PER_PASS = lambda iters: 5 + iters + 1 + 2 + 1  # noqa: E731  (prep x3, pyramid x2, lookups, upsample, scale, warp, epe)
 
 
 class HostStagedRunner:
