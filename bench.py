@@ -401,7 +401,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=8, help="image pairs per GPU per step")
     ap.add_argument("--micro", type=int, default=8, help="pairs per pyramid build (device-resident arm)")
-    ap.add_argument("--e2e-micro", type=int, default=2, help="pairs per staged micro-batch (host arm)")
+    ap.add_argument("--e2e-micro", type=int, default=1, help="pairs per staged micro-batch (host arm)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cta-group", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -25,12 +25,13 @@ if "warp" in which:
         for _ in range(reps):
             warp(frame, flow, return_mask=True, variant=v)
 if "corr" in which or "lookup" in which:
-    b, c, h, w = 16, 256, 55, 128
+    b, c, h, w = (4, 256, 136, 240) if "c5" in which else (16, 256, 55, 128)
     f1 = torch.randn((b, c, h, w), device="cuda", generator=gen)
     f2 = torch.randn((b, c, h, w), device="cuda", generator=gen)
     for cg in (1, 2):
         for _ in range(reps):
             blk = CorrBlock(f1, f2, cta_group=cg)
+    blk = CorrBlock(f1, f2)
     coords = coords_grid(b, h, w).cuda() + 4 * torch.randn((b, 2, h, w), device="cuda", generator=gen)
     if "lookup" in which:
         for _ in range(reps):

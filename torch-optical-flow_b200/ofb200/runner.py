@@ -118,7 +118,13 @@ class HostStagedRunner:
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self.freed[slot])       # previous user of this slot has finished
             for k in FIELDS:
-                self.slots[slot][k].copy_(src[k], non_blocking=True)
+                if k == "coords":
+                    # (iters, pairs, 2, h, w): a pair range is contiguous per iteration, not as a whole --
+                    # copy iteration by iteration so every transfer is one pinned, asynchronous DMA
+                    for it in range(src[k].shape[0]):
+                        self.slots[slot][k][it].copy_(src[k][it], non_blocking=True)
+                else:
+                    self.slots[slot][k].copy_(src[k], non_blocking=True)
                 self.h2d_bytes += src[k].numel() * src[k].element_size()
             self.ready[slot].record(self.copy_stream)
 
