@@ -196,6 +196,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core (numpy / the
+    # oracle library are imported after this point, so the setting takes effect)
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = str(host_cores())
     steps, warm = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
     cb = time_cpu(steps, warm, 1)
     line = {
