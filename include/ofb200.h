@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define OFB_VERSION 100
+#define OFB_VERSION 110
 
 #define OFB_OK 0
 #define OFB_EINVAL (-1)       /* bad size / null pointer / unsupported enum value          */
@@ -108,14 +108,22 @@ int ofb_epe_map_f32(const float* pred, const float* target, float* out, int B, i
 
 /* ---------------------------------------------------------------------------------------
  * Correlation pyramid layout (owned by the caller, described by ofb_pyramid_layout).
- * Level l of query q = (b, y, x) is an h_l x w_l image, h_l = floor(h / 2^l):
- *     element (q, yy, xx) lives at  base[l] + q * q_stride[l] + yy * row_pitch[l] + xx
- * (strides in ELEMENTS of the pyramid dtype).  ofb_pyramid_layout fills the strides the
- * tensor-core builder needs (row_pitch multiple of 16 elements so every row starts on a 32-byte
- * sector, q_stride multiple of 8; the builder writes whole 8-element pieces, i.e. zeros into the
- * row padding) and
- * returns the total element count per level through elems[l] (= B*h*w*q_stride[l]).
+ * Level l of query q = (b, y, x) is an h_l x w_l image, h_l = floor(h / 2^l).  Two layouts
+ * (strides in ELEMENTS of the pyramid dtype, `np` = row_pitch):
+ *   OFB_LAYOUT_ROWS      element (q, yy, xx) at  base[l] + q*q_stride[l] + yy*np + xx
+ *   OFB_LAYOUT_BLOCK8X4  8 (x) by 4 (y) element blocks of 32 contiguous elements (64 bytes in bf16 = one
+ *                        DRAM atom), blocks raster-ordered:
+ *                        base[l] + q*q_stride[l] + ((yy>>2)*(np>>3) + (xx>>3))*32 + (yy&3)*8 + (xx&7)
+ *                        -- the lookup's 11x11 window touches ~8 atoms instead of ~15.
+ * ofb_pyramid_layout fills the strides: mode 0 = tight rows (row_pitch = w_l), 1 = padded rows
+* (row_pitch multiple of 16 elements, so every row starts on a 32-byte sector), 2 = padded 8x4
+ * blocks (row_pitch multiple of 8, rows padded to a multiple of 4).  elems[l] receives q_stride[l].
+ * The tensor-core builder needs mode 1 or 2 and writes whole 8-element pieces, i.e. zeros into the
+ * padding columns; the bf16 lookup kernel relies on padding columns holding finite values.
  * ------------------------------------------------------------------------------------- */
+#define OFB_LAYOUT_ROWS 0
+#define OFB_LAYOUT_BLOCK8X4 1
+
 typedef struct ofb_pyramid {
     void* base[OFB_MAX_LEVELS];
     int64_t q_stride[OFB_MAX_LEVELS];
@@ -123,10 +131,12 @@ typedef struct ofb_pyramid {
     int32_t lvl_h[OFB_MAX_LEVELS];
     int32_t lvl_w[OFB_MAX_LEVELS];
     int32_t levels;
-    int32_t dtype; /* OFB_DTYPE_F32 or OFB_DTYPE_BF16 */
+    int32_t dtype;  /* OFB_DTYPE_F32 or OFB_DTYPE_BF16 */
+    int32_t layout; /* OFB_LAYOUT_ROWS or OFB_LAYOUT_BLOCK8X4 (bf16 only) */
+    int32_t reserved;
 } ofb_pyramid;
 
-int ofb_pyramid_layout(int h, int w, int levels, int padded, ofb_pyramid* pyr_host, int64_t elems_host[OFB_MAX_LEVELS]);
+int ofb_pyramid_layout(int h, int w, int levels, int mode, ofb_pyramid* pyr_host, int64_t elems_host[OFB_MAX_LEVELS]);
 
 /* ---------------------------------------------------------------------------------------
  * K2  all-pairs correlation pyramid.  Replaces CorrBlock.corr + CorrBlock.__init__

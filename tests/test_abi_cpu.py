@@ -30,7 +30,7 @@ def test_every_header_symbol_is_exported_and_bound(lib):
     for s in syms:
         assert hasattr(raw, s), f"{s} declared in include/ofb200.h but not exported"
         assert s in ofb200.SIGNATURES, f"{s} has no ctypes signature"
-    assert lib.ofb_version() == 100
+    assert lib.ofb_version() == 110
     assert lib.ofb_strerror(0) == b"ok"
     assert b"invalid" in lib.ofb_strerror(-1)
 
@@ -42,8 +42,16 @@ def test_pyramid_layout_is_host_only(lib):
     assert [pyr.lvl_h[i] for i in range(4)] == [47, 23, 11, 5]
     assert [pyr.lvl_w[i] for i in range(4)] == [156, 78, 39, 19]       # floor: trailing odd rows / cols dropped
     for i in range(4):
-        assert pyr.row_pitch[i] % 8 == 0 and pyr.row_pitch[i] >= pyr.lvl_w[i]
+        assert pyr.row_pitch[i] % 16 == 0 and pyr.row_pitch[i] >= pyr.lvl_w[i]
         assert pyr.q_stride[i] % 8 == 0 and pyr.q_stride[i] >= pyr.row_pitch[i] * pyr.lvl_h[i]
+    assert pyr.layout == ofb200.LAYOUT_ROWS
+    assert lib.ofb_pyramid_layout(47, 156, 4, 2, ctypes.byref(pyr), ctypes.byref(elems)) == 0
+    assert pyr.layout == ofb200.LAYOUT_BLOCK8X4
+    for i in range(4):      # 8x4 blocks: rows padded to a multiple of 4, columns to a multiple of 8
+        assert pyr.row_pitch[i] == (pyr.lvl_w[i] + 7) // 8 * 8
+        assert pyr.q_stride[i] == pyr.row_pitch[i] * ((pyr.lvl_h[i] + 3) // 4 * 4)
+    assert lib.ofb_pyramid_layout(47, 156, 4, 0, ctypes.byref(pyr), ctypes.byref(elems)) == 0
+    assert [pyr.row_pitch[i] for i in range(4)] == [156, 78, 39, 19]
     assert lib.ofb_pyramid_layout(4, 4, 4, 1, ctypes.byref(pyr), ctypes.byref(elems)) != 0   # level 3 would be empty
     assert lib.ofb_pyramid_layout(8, 8, 5, 1, ctypes.byref(pyr), ctypes.byref(elems)) != 0
 

@@ -315,8 +315,9 @@ def test_epe_vs_oracle(shape):
 
 
 # =============================================================================== K3 lookup
-def _pyramid_from_numpy(levels, dtype):
-    """Wrap oracle-built fp32 levels into a CorrBlock-like object that owns padded device buffers."""
+def _pyramid_from_numpy(levels, dtype, blocked=False):
+    """Wrap oracle-built fp32 levels into a CorrBlock-like object that owns padded device buffers
+    (padded rows, or the 8x4-blocked layout of include/ofb200.h)."""
     import ctypes
 
     import ofb200
@@ -325,10 +326,24 @@ def _pyramid_from_numpy(levels, dtype):
     pyr = ofb200.Pyramid()
     pyr.levels = len(levels)
     pyr.dtype = ofb200.DTYPE_BF16 if dtype == torch.bfloat16 else ofb200.DTYPE_F32
+    pyr.layout = ofb200.LAYOUT_BLOCK8X4 if blocked else ofb200.LAYOUT_ROWS
     bufs = []
     for l, lv in enumerate(levels):
         hl, wl = lv.shape[-2:]
         pitch = (wl + 15) & ~15
+        if blocked:
+            pitch = (wl + 7) & ~7
+            rows = (hl + 3) & ~3
+            img = torch.full((q, rows, pitch), 3.0e38, dtype=dtype, device="cuda")
+            img[:, :hl, :wl] = T(lv[:, 0]).to(dtype)
+            buf = img.view(q, rows // 4, 4, pitch // 8, 8).permute(0, 1, 3, 2, 4).contiguous()   # (q, by, bx, y, x)
+            bufs.append(buf)
+            pyr.base[l] = buf.data_ptr()
+            pyr.q_stride[l] = rows * pitch
+            pyr.row_pitch[l] = pitch
+            pyr.lvl_h[l] = hl
+            pyr.lvl_w[l] = wl
+            continue
         # fp32 kernel: pads must never be read (NaN).  bf16 register-tile kernel: pads may be read but must
         # not reach the output -- the contract is "finite", so poison them with a huge finite value
         poison = float("nan") if dtype == torch.float32 else 3.0e38
@@ -383,10 +398,13 @@ def test_lookup_golden_odd_radius3(golden):
     assert np.array_equal(idx, g["odd_idx"]) and np.array_equal(valid, g["odd_valid"])
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, "bf16_blocked"])
 @pytest.mark.parametrize("hw", [(47, 156), (55, 128), (24, 40)])
 def test_lookup_vs_oracle(dtype, hw):
     """Seeded pyramid + coords (integer coords, sub-pixel noise, far out of range) vs the oracle."""
+    blocked = dtype == "bf16_blocked"
+    if blocked:
+        dtype = torch.bfloat16
     h, w = hw
     b = 1
     r = rng(8)
@@ -394,7 +412,7 @@ def test_lookup_vs_oracle(dtype, hw):
     levels = [r.standard_normal((q, 1, h >> l, w >> l)).astype(np.float32) for l in range(4)]
     if dtype == torch.bfloat16:
         levels = [oracle.round_bf16(lv) for lv in levels]          # same stored values on both sides
-    pyr, bufs = _pyramid_from_numpy(levels, dtype)
+    pyr, bufs = _pyramid_from_numpy(levels, dtype, blocked)
     grid = oracle.coords_grid(b, h, w)
     for kind in ("int", "noise", "far", "half", "edge", "nonfinite"):
         coords = grid.copy()
@@ -499,6 +517,29 @@ def test_corr_pyramid_tcgen05_vs_fp32(cta_group, shape):
             assert maxabs(a, o) <= 2e-4
     for lvl, (rel, mx) in enumerate(_pyr_errors(blk.corr_pyramid, refs)):
         assert rel <= 4e-3 and mx <= 4e-2, (lvl, rel, mx)
+
+
+def test_corr_block_is_immune_to_poisoned_allocator_memory():
+    """The lookup kernel may read the padding of the pyramid buffers (with zero weights): whatever the
+    caching allocator hands back, the builder must have left finite values there."""
+    from model.corr import CorrBlock
+    from model.utils import coords_grid
+
+    gen = torch.Generator(device="cuda").manual_seed(21)
+    b, c, h, w = 1, 64, 19, 37                                  # odd sizes: every level has padding
+    f1 = torch.randn((b, c, h, w), device="cuda", generator=gen)
+    f2 = torch.randn((b, c, h, w), device="cuda", generator=gen)
+    ref = CorrBlock(f1, f2, pyramid_dtype=torch.float32, builder="simt")
+    coords = coords_grid(b, h, w).cuda() + 3 * torch.randn((b, 2, h, w), device="cuda", generator=gen)
+    want = ref(coords)
+    for _ in range(3):
+        poison = torch.full((64 << 20,), float("nan"), dtype=torch.bfloat16, device="cuda")
+        del poison                                               # back to the caching allocator, NaN-filled
+        blk = CorrBlock(f1, f2)
+        got = blk(coords)
+        assert torch.isfinite(got).all()
+        assert float((got - want).norm() / want.norm()) <= 6e-3
+        del blk
 
 
 def test_corr_volume_static_and_errors():

@@ -129,7 +129,7 @@ def bench_lookup(name, blk, gen, b, h, w, iters=12):
     n = h * w
     coords = coords_grid(b, h, w).cuda()[None] + 4 * torch.randn((iters, b, 2, h, w), device="cuda", generator=gen)
     out = torch.empty((b, 324, h, w), device="cuda")
-    esz = 2 if blk.corr_pyramid[0].dtype == torch.bfloat16 else 4
+    esz = 2 if blk._buffers[0].dtype == torch.bfloat16 else 4
 
     def look():
         for it in range(iters):

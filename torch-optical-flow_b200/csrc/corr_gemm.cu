@@ -72,13 +72,20 @@ struct LevelOut {
     __nv_bfloat16* base;
     long long q_stride;
     int pitch, h, w;
+    int blocked;                 // OFB_LAYOUT_BLOCK8X4: a 16-byte piece is one row of an 8x4 block
 };
+// element offset of the 8-element piece starting at (y, x), x % 8 == 0
+__device__ __forceinline__ long long piece_offset(const LevelOut& L, int y, int x) {
+    if (L.blocked) return ((long long)(y >> 2) * (L.pitch >> 3) + (x >> 3)) * 32 + (y & 3) * 8;
+    return (long long)y * L.pitch + x;
+}
 
 struct GemmParams {
     int B, C, kb;
     int Nq;                      // queries per batch element (rows of the volume)
     int th, tw;                  // target image of THIS run (h x w, or h/4 x w/4 for the pooled run)
-    int XH, PH;                  // tile = (32*XH) x PH targets, XH*PH = 8
+    int CW, CR;                  // chunk = CW x CR targets (64): 32 x 2 for row layouts, 16 x 4 for 8x4-blocked layouts
+    int XB, YQ;                  // tile = XB x YQ chunks (XB * YQ = 4) = (CW*XB) x (CR*YQ) targets
     int nbox, box_rows;          // TMA boxes per stage and CTA, rows per box
     int ntx, nty, ntiles;
     int tiles_per_item, n_chunks, mblk, n_items;
@@ -292,7 +299,7 @@ __device__ __forceinline__ ItemCoord decode_item(const GemmParams& P, int item) 
 }
 
 // ------------------------------------------------------------------------------------ the kernel
-template <int CG, bool PROF>
+template <int CG, bool PROF, bool BLK>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const GemmParams P) {
@@ -344,9 +351,10 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (lane == 0) {
             const uint32_t full_a = (CG == 2) ? map_to_rank(bar_a_full, 0) : bar_a_full;
             // which part of the tile this CTA fetches (cta_group 2: chunks {2*rank, 2*rank+1})
-            const int xh0 = (CG == 2 && P.XH >= 2) ? (int)rank * (P.XH / 2) : 0;
-            const int yoff = (CG == 2 && P.XH == 1) ? (int)rank * (P.PH / 2) : 0;
-            const int box_bytes = 32 * P.box_rows * 128;
+            const int TH = P.CR * P.YQ;
+            const int xb0 = (CG == 2 && P.XB >= 2) ? (int)rank * (P.XB / 2) : 0;
+            const int yoff = (CG == 2 && P.XB == 1) ? (int)rank * (TH / 2) : 0;
+            const int box_bytes = P.CW * P.box_rows * 128;
             const uint64_t pol = l2_policy_evict_last();
             uint32_t stage = 0, bphase = 0, aphase = 0;
             for (int item = worker; item < P.n_items; item += n_workers) {
@@ -361,14 +369,14 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 const int t1 = min(t0 + P.tiles_per_item, P.ntiles);
                 for (int t = t0; t < t1; ++t) {
                     const int ty = t / P.ntx, tx = t - ty * P.ntx;
-                    const int x0 = (tx * P.XH + xh0) * 32, y0 = ty * P.PH + yoff;
+                    const int x0 = (tx * P.XB + xb0) * P.CW, y0 = ty * TH + yoff;
                     for (int kb = 0; kb < P.kb; ++kb) {
                         mbar_wait_p<PROF>(bar_b_empty + 8 * stage, bphase ^ 1, pw0);
                         const uint32_t full_b = (CG == 2) ? map_to_rank(bar_b_full + 8 * stage, 0) : bar_b_full + 8 * stage;
                         if (leader) mbar_expect_tx(bar_b_full + 8 * stage, (uint32_t)B_TILE_KB_BYTES);
                         const uint32_t dst = sbase + OFF_B + stage * B_STAGE_BYTES;
                         for (int j = 0; j < P.nbox; ++j)
-                            tma_load_4d<CG>(dst + j * box_bytes, &map_b, full_b, kb * BLOCK_K, x0 + 32 * j, y0, ic.b, pol);
+                            tma_load_4d<CG>(dst + j * box_bytes, &map_b, full_b, kb * BLOCK_K, x0 + P.CW * j, y0, ic.b, pol);
                         if (++stage == B_STAGES) { stage = 0; bphase ^= 1; }
                     }
                 }
@@ -427,12 +435,15 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int half = (warp - 2) >> 2;
         const uint32_t stg_a = sbase + R::OFF_STG + (warp - 2) * STG_WARP_BYTES;
         const uint32_t stg_b = stg_a + STG_A_BYTES;
-        const int ypairs = P.PH >> 1;
         // write side of the transposes: this lane's query row, 16-byte pieces XOR-swizzled
         const uint32_t wa = stg_a + (uint32_t)lane * 128u, wsw_a = (uint32_t)(lane & 7);
         const uint32_t wb = stg_b + (uint32_t)lane * 32u, wsw_b = (uint32_t)((lane >> 2) & 1);
-        // read side: level A -- 8 lanes per query (2 rows x 4 pieces), 4 queries per instruction
-        const int ra_q = lane >> 3, ra_p = lane & 7;
+        // read side: level A -- 8 lanes per query, 4 queries per instruction.  Lanes follow MEMORY order:
+        // rows: piece p = (row p>>2, columns 8*(p&3));  8x4 blocks: memory piece m = (block m>>2, block row m&3)
+        // is register piece p = (row p>>1, block p&1) -- the chunk's two blocks are one contiguous 128-byte line
+        const int ra_q = lane >> 3;
+        const int ra_p = BLK ? ((((lane & 7) & 3) << 1) | ((lane & 7) >> 2)) : (lane & 7);
+        const int ra_dy = BLK ? (ra_p >> 1) : (ra_p >> 2), ra_dx = BLK ? (ra_p & 1) * 8 : (ra_p & 3) * 8;
         // level B -- 2 lanes per query, 16 queries per instruction
         const int rb_q = lane >> 1, rb_p = lane & 1;
         uint32_t acc = 0, tphase = 0;
@@ -488,8 +499,11 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                             // 2x2 means, summed in the reference's raster order then / 4 (corr.py:53)
                             float m[16];
 #pragma unroll
-                            for (int c = 0; c < 16; ++c)
-                                m[c] = (((f[2 * c] + f[2 * c + 1]) + f[32 + 2 * c]) + f[32 + 2 * c + 1]) * 0.25f;
+                            for (int c = 0; c < 16; ++c) {
+                                // row layouts: chunk 2 x 32 -> one pooled row of 16; blocked: chunk 4 x 16 -> 2 rows of 8
+                                const int a = BLK ? ((c >> 3) * 32 + (c & 7) * 2) : 2 * c, dn = BLK ? 16 : 32;
+                                m[c] = (((f[a] + f[a + 1]) + f[a + dn]) + f[a + dn + 1]) * 0.25f;
+                            }
 #pragma unroll
                             for (int p = 0; p < 2; ++p) {
                                 const float* s = m + p * 8;
@@ -500,16 +514,16 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     }
                     __syncwarp();
                     // ---- stage -> global, 16-byte pieces, 64-byte segments per (query, image row)
-                    const int xh = k / ypairs, yp = k - xh * ypairs;
-                    const int x0 = (tx * P.XH + xh) * 32, y0 = ty * P.PH + 2 * yp;
+                    const int xb = k / P.YQ, yq = k - xb * P.YQ;
+                    const int x0 = (tx * P.XB + xb) * P.CW, y0 = (ty * P.YQ + yq) * P.CR;
                     if (!(PROF && (dbg & 1))) {
-                        const int y = y0 + (ra_p >> 2), x = x0 + (ra_p & 3) * 8;
+                        const int y = y0 + ra_dy, x = x0 + ra_dx;
                         // pieces are always written whole and the row padding (w..pitch) is written too: TMA
                         // zero-fills targets outside the image, so the padding receives zeros (finite values --
                         // the lookup kernel relies on that) and no 32-byte sector is left partially written
                         // (partial sectors measured a 2x slowdown of the whole kernel at w = 156)
                         const bool in_img = y < P.la.h && x < P.la.pitch;
-                        const long long off_yx = (long long)y * P.la.pitch + x;
+                        const long long off_yx = piece_offset(P.la, y, x);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const int r = j * 4 + ra_q;
@@ -520,9 +534,10 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         }
                     }
                     if (P.has_b && !(PROF && (dbg & 2))) {
-                        const int y = y0 >> 1, x = (x0 >> 1) + rb_p * 8;
+                        // pooled chunk: rows layout 1 x 16 (pieces side by side); blocked 2 x 8 (pieces = 2 block rows)
+                        const int y = (y0 >> 1) + (BLK ? rb_p : 0), x = (x0 >> 1) + (BLK ? 0 : rb_p * 8);
                         const bool in_img = y < P.lb.h && x < P.lb.pitch;
-                        const long long off_yx = (long long)y * P.lb.pitch + x;
+                        const long long off_yx = piece_offset(P.lb, y, x);
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
                             const int r = j * 16 + rb_q;
@@ -579,11 +594,11 @@ bool encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims
     return r == CUDA_SUCCESS;
 }
 
-template <int CG, bool PROF>
+template <int CG, bool PROF, bool BLK>
 int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& P, int grid, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        OFB_CUDA(cudaFuncSetAttribute(corr_pyramid_kernel<CG, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        OFB_CUDA(cudaFuncSetAttribute(corr_pyramid_kernel<CG, PROF, BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Ring<CG>::SMEM_ALLOC));
         configured = true;
     }
@@ -599,7 +614,7 @@ int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    OFB_CUDA(cudaLaunchKernelEx(&cfg, corr_pyramid_kernel<CG, PROF>, ma, mb, P));
+    OFB_CUDA(cudaLaunchKernelEx(&cfg, corr_pyramid_kernel<CG, PROF, BLK>, ma, mb, P));
     OFB_LAUNCH_CHECK();
     return OFB_OK;
 }
@@ -611,16 +626,26 @@ int run_gemm(const void* f1_km, const void* f2_km, const ofb_pyramid* pyr, int l
     GemmParams P = {};
     P.B = B; P.C = C; P.kb = C / BLOCK_K; P.Nq = Nq; P.th = th; P.tw = tw;
     P.scale = scale; P.apply_scale = (scale != 1.0f) ? 1 : 0;
-    // tile shape: 32x8, 64x4 or 128x2 targets -- the one that covers the image with the fewest tiles
+    // chunk shape follows the output layout (a chunk must be whole 64/128-byte runs of it); tile shape =
+    // the arrangement of 4 chunks that covers the image with the fewest tiles (ties: the widest)
+    const bool blk = pyr->layout == OFB_LAYOUT_BLOCK8X4;
+    P.CW = blk ? 16 : 32; P.CR = blk ? 4 : 2;
     long long best = -1;
-    for (int xh = 1; xh <= 4; xh *= 2) {
-        const int ph = 8 / xh;
-        const long long tiles = (long long)((tw + 32 * xh - 1) / (32 * xh)) * ((th + ph - 1) / ph);
-        if (best < 0 || tiles <= best) { best = tiles; P.XH = xh; P.PH = ph; }   // ties: the widest tile (longer runs per row)
+    for (int xb = 1; xb <= 4; xb *= 2) {
+        const int yq = 4 / xb;
+        const long long tiles = (long long)((tw + P.CW * xb - 1) / (P.CW * xb)) * ((th + P.CR * yq - 1) / (P.CR * yq));
+        // measured (C3, C4, C5; profiles/): rows layout is fastest with the widest tile, blocked with 2 x 2 chunks
+        const long long cost = tiles * 100 + (blk ? (xb == 2 ? 0 : 2 * tiles) : (4 - xb));
+        if (best < 0 || cost < best) { best = cost; P.XB = xb; P.YQ = yq; }
     }
-    P.ntx = (tw + 32 * P.XH - 1) / (32 * P.XH); P.nty = (th + P.PH - 1) / P.PH; P.ntiles = P.ntx * P.nty;
-    if (cg == 2) { P.nbox = P.XH >= 2 ? P.XH / 2 : 1; P.box_rows = P.XH == 1 ? P.PH / 2 : P.PH; }
-    else { P.nbox = P.XH; P.box_rows = P.PH; }
+    if (const char* e = getenv("OFB_K2_XB")) {           // tuning override: chunks per tile row (1, 2 or 4)
+        const int xb = atoi(e);
+        if (xb == 1 || xb == 2 || xb == 4) { P.XB = xb; P.YQ = 4 / xb; }
+    }
+    const int TW = P.CW * P.XB, TH = P.CR * P.YQ;
+    P.ntx = (tw + TW - 1) / TW; P.nty = (th + TH - 1) / TH; P.ntiles = P.ntx * P.nty;
+    if (cg == 2) { P.nbox = P.XB >= 2 ? P.XB / 2 : 1; P.box_rows = P.XB == 1 ? TH / 2 : TH; }
+    else { P.nbox = P.XB; P.box_rows = TH; }
     P.mblk = (Nq + BLOCK_M * cg - 1) / (BLOCK_M * cg);
     const int workers = ofb_num_sms() / cg;
     // split the target tiles of one (batch, query block) into chunks so the last wave is not mostly idle:
@@ -642,12 +667,12 @@ int run_gemm(const void* f1_km, const void* f2_km, const ofb_pyramid* pyr, int l
     P.n_items = (int)n_items;
     P.la.base = reinterpret_cast<__nv_bfloat16*>(pyr->base[la_idx]);
     P.la.q_stride = pyr->q_stride[la_idx]; P.la.pitch = pyr->row_pitch[la_idx];
-    P.la.h = pyr->lvl_h[la_idx]; P.la.w = pyr->lvl_w[la_idx];
+    P.la.h = pyr->lvl_h[la_idx]; P.la.w = pyr->lvl_w[la_idx]; P.la.blocked = pyr->layout == OFB_LAYOUT_BLOCK8X4;
     P.has_b = lb_idx >= 0 ? 1 : 0;
     if (P.has_b) {
         P.lb.base = reinterpret_cast<__nv_bfloat16*>(pyr->base[lb_idx]);
         P.lb.q_stride = pyr->q_stride[lb_idx]; P.lb.pitch = pyr->row_pitch[lb_idx];
-        P.lb.h = pyr->lvl_h[lb_idx]; P.lb.w = pyr->lvl_w[lb_idx];
+        P.lb.h = pyr->lvl_h[lb_idx]; P.lb.w = pyr->lvl_w[lb_idx]; P.lb.blocked = P.la.blocked;
     }
     P.prof = prof ? prof + (size_t)prof_slot * PROF_SLOT : nullptr;
     P.dbg = 0;
@@ -666,17 +691,17 @@ int run_gemm(const void* f1_km, const void* f2_km, const ofb_pyramid* pyr, int l
     {
         const uint64_t dims[4] = {(uint64_t)C, (uint64_t)tw, (uint64_t)th, (uint64_t)B};
         const uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)tw * C * 2, (uint64_t)th * tw * C * 2};
-        const uint32_t box[4] = {BLOCK_K, 32, (uint32_t)P.box_rows, 1};
+        const uint32_t box[4] = {BLOCK_K, (uint32_t)P.CW, (uint32_t)P.box_rows, 1};
         if (!encode_map(&mb, f2_km, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return OFB_EDRIVER;
     }
     int grid = workers * cg;
     if ((long long)grid > n_items * cg) grid = (int)(n_items * cg);
-    if (prof) {
-        if (cg == 2) return launch_gemm<2, true>(ma, mb, P, grid, st);
-        return launch_gemm<1, true>(ma, mb, P, grid, st);
-    }
-    if (cg == 2) return launch_gemm<2, false>(ma, mb, P, grid, st);
-    return launch_gemm<1, false>(ma, mb, P, grid, st);
+#define OFB_GEMM_CASE(CGV, PROFV, BLKV) \
+    if (cg == CGV && (prof != nullptr) == PROFV && blk == BLKV) return launch_gemm<CGV, PROFV, BLKV>(ma, mb, P, grid, st);
+    OFB_GEMM_CASE(1, false, false) OFB_GEMM_CASE(1, false, true) OFB_GEMM_CASE(2, false, false) OFB_GEMM_CASE(2, false, true)
+    OFB_GEMM_CASE(1, true, false) OFB_GEMM_CASE(1, true, true) OFB_GEMM_CASE(2, true, false) OFB_GEMM_CASE(2, true, true)
+#undef OFB_GEMM_CASE
+    return OFB_EINVAL;
 }
 
 int corr_pyramid_impl(const void* f1_km, const void* f2_km, const void* f2q_km, const ofb_pyramid* pyr, int B, int C, int h,
@@ -697,8 +722,10 @@ int corr_pyramid_impl(const void* f1_km, const void* f2_km, const void* f2q_km, 
         // 16-byte store pieces: rows and query slices start on 8-element boundaries
         if ((pyr->row_pitch[l] & 7) || (pyr->q_stride[l] & 7) || (reinterpret_cast<uintptr_t>(pyr->base[l]) & 15))
             return OFB_EALIGN;
-        if (pyr->q_stride[l] < (int64_t)pyr->row_pitch[l] * pyr->lvl_h[l]) return OFB_EINVAL;
+        const int rows = pyr->layout == OFB_LAYOUT_BLOCK8X4 ? ((pyr->lvl_h[l] + 3) & ~3) : pyr->lvl_h[l];
+        if (pyr->q_stride[l] < (int64_t)pyr->row_pitch[l] * rows) return OFB_EINVAL;
     }
+    if (pyr->layout != OFB_LAYOUT_ROWS && pyr->layout != OFB_LAYOUT_BLOCK8X4) return OFB_EINVAL;
     // auto: one CTA per tile -- measured faster than the CTA pair on every BASELINE shape once the
     // kernel became HBM-write-bound (profiles/r01_k2_findings.md); the pair halves operand traffic but
     // couples two epilogues through one accumulator barrier

@@ -163,9 +163,11 @@ OFB_API int ofb_corr_prep_bf16(const float* fmap_nchw, void* out_km_bf16, int B,
     return OFB_OK;
 }
 
-OFB_API int ofb_pyramid_layout(int h, int w, int levels, int padded, ofb_pyramid* pyr, int64_t elems[OFB_MAX_LEVELS]) {
-    if (!pyr || h <= 0 || w <= 0 || levels < 1 || levels > OFB_MAX_LEVELS) return OFB_EINVAL;
+OFB_API int ofb_pyramid_layout(int h, int w, int levels, int mode, ofb_pyramid* pyr, int64_t elems[OFB_MAX_LEVELS]) {
+    if (!pyr || h <= 0 || w <= 0 || levels < 1 || levels > OFB_MAX_LEVELS || mode < 0 || mode > 2) return OFB_EINVAL;
     pyr->levels = levels;
+    pyr->layout = mode == 2 ? OFB_LAYOUT_BLOCK8X4 : OFB_LAYOUT_ROWS;
+    pyr->reserved = 0;
     for (int l = 0; l < OFB_MAX_LEVELS; ++l) {
         pyr->base[l] = nullptr;
         pyr->q_stride[l] = 0; pyr->row_pitch[l] = 0; pyr->lvl_h[l] = 0; pyr->lvl_w[l] = 0;
@@ -174,9 +176,11 @@ OFB_API int ofb_pyramid_layout(int h, int w, int levels, int padded, ofb_pyramid
     for (int l = 0; l < levels; ++l) {
         const int hl = h >> l, wl = w >> l;
         if (hl <= 0 || wl <= 0) return OFB_EINVAL;   // F.avg_pool2d raises "Output size is too small" (corr.py:53)
-        const int pitch = padded ? ((wl + 15) & ~15) : wl;   // rows start on 32-byte sectors (bf16)
+        // padded rows start on 32-byte sectors (bf16); 8x4 blocks are 64-byte aligned by construction
+        const int pitch = mode == 1 ? ((wl + 15) & ~15) : mode == 2 ? ((wl + 7) & ~7) : wl;
+        const int rows = mode == 2 ? ((hl + 3) & ~3) : hl;
         pyr->lvl_h[l] = hl; pyr->lvl_w[l] = wl; pyr->row_pitch[l] = pitch;
-        pyr->q_stride[l] = (int64_t)pitch * hl;
+        pyr->q_stride[l] = (int64_t)pitch * rows;
         if (elems) elems[l] = pyr->q_stride[l];      // per query; caller multiplies by B*h*w
     }
     return OFB_OK;
@@ -186,6 +190,7 @@ OFB_API int ofb_corr_pyramid_simt_f32(const float* fmap1, const float* fmap2, co
                                       int h, int w, float scale, void* stream) {
     if (!fmap1 || !fmap2 || !pyr || B < 0 || C <= 0 || h <= 0 || w <= 0) return OFB_EINVAL;
     if (pyr->levels < 1 || pyr->levels > OFB_MAX_LEVELS) return OFB_EINVAL;
+    if (pyr->layout != OFB_LAYOUT_ROWS) return OFB_EUNSUPPORTED;      // the CUDA-core builder writes rows
     for (int l = 0; l < pyr->levels; ++l)
         if (!pyr->base[l] || pyr->lvl_h[l] != (h >> l) || pyr->lvl_w[l] != (w >> l) || pyr->row_pitch[l] < pyr->lvl_w[l])
             return OFB_EINVAL;

@@ -43,6 +43,7 @@ struct LookupParams {
     int lh[OFB_MAX_LEVELS];
     int lw[OFB_MAX_LEVELS];
     int levels, radius, B, h, w;
+    int blocked;   // OFB_LAYOUT_BLOCK8X4 (register-tile kernel only)
 };
 
 template <typename T> struct Elem;
@@ -311,11 +312,15 @@ __global__ void __launch_bounds__(128) lookup_tile_kernel(const LookupParams P, 
     auto load_row = [&](int r) {
         const int y = ys + r;
         const bool rok = !dead && y >= 0 && y < Hl;
-        const __nv_bfloat16* row = slice + (long long)y * pitch + xa;
+        // an aligned 8-element chunk is one row of an 8x4 block (blocked) or 8 consecutive row elements
+        const __nv_bfloat16* row = P.blocked
+            ? slice + ((long long)(y >> 2) * (pitch >> 3) + (xa >> 3)) * 32 + (y & 3) * 8
+            : slice + (long long)y * pitch + xa;
+        const int cstep = P.blocked ? 32 : 8;
         c0v = make_uint4(0, 0, 0, 0); c1v = make_uint4(0, 0, 0, 0); c2v = make_uint2(0, 0);
         if (rok && ck0) c0v = __ldg(reinterpret_cast<const uint4*>(row));
-        if (rok && ck1) c1v = __ldg(reinterpret_cast<const uint4*>(row + 8));
-        if (rok && ck2) c2v = __ldg(reinterpret_cast<const uint2*>(row + 16));
+        if (rok && ck1) c1v = __ldg(reinterpret_cast<const uint4*>(row + cstep));
+        if (rok && ck2) c2v = __ldg(reinterpret_cast<const uint2*>(row + 2 * cstep));
     };
     load_row(0);
 #pragma unroll
@@ -402,6 +407,8 @@ OFB_API int ofb_corr_lookup(const ofb_pyramid* pyr, const float* coords, float* 
     if (B == 0) return OFB_OK;
     LookupParams P;
     P.levels = pyr->levels; P.radius = radius; P.B = B; P.h = h; P.w = w;
+    P.blocked = pyr->layout == OFB_LAYOUT_BLOCK8X4;
+    if (pyr->layout != OFB_LAYOUT_ROWS && pyr->layout != OFB_LAYOUT_BLOCK8X4) return OFB_EINVAL;
     for (int l = 0; l < OFB_MAX_LEVELS; ++l) {
         const bool on = l < pyr->levels;
         P.base[l] = on ? pyr->base[l] : nullptr;
@@ -434,6 +441,7 @@ OFB_API int ofb_corr_lookup(const ofb_pyramid* pyr, const float* coords, float* 
         OFB_LAUNCH_CHECK();
         return OFB_OK;
     }
+    if (P.blocked) return OFB_EUNSUPPORTED;   // the generic kernels read rows
     if (pyr->dtype == OFB_DTYPE_BF16) {
         OFB_CUDA(cudaFuncSetAttribute(lookup_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         lookup_kernel<__nv_bfloat16><<<(int)blocks, NW * 32, smem, st>>>(P, coords, out, idx_or_null, valid_or_null);

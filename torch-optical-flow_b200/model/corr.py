@@ -55,7 +55,6 @@ class CorrBlock:
     ) -> None:
         self.num_levels = num_levels
         self.radius = radius
-        self.corr_pyramid: List[Tensor] = []
         if fmap1.shape != fmap2.shape or fmap1.dim() != 4:
             raise RuntimeError("CorrBlock: fmap1 and fmap2 must both be (B, C, h, w)")
         if not (1 <= num_levels <= ofb200.MAX_LEVELS):
@@ -86,10 +85,14 @@ class CorrBlock:
 
         pyr = ofb200.Pyramid()
         elems = (ctypes.c_int64 * ofb200.MAX_LEVELS)()
-        ofb200.check(lib.ofb_pyramid_layout(h, w, num_levels, 1, ctypes.byref(pyr), ctypes.byref(elems)), "ofb_pyramid_layout")
+        # tcgen05 builder: 8x4-blocked bf16 levels (what the lookup kernel reads with the fewest DRAM atoms);
+        # CUDA-core builder: padded rows
+        mode = 2 if (builder == "tcgen05" and radius in (3, 4)) else 1
+        ofb200.check(lib.ofb_pyramid_layout(h, w, num_levels, mode, ctypes.byref(pyr), ctypes.byref(elems)), "ofb_pyramid_layout")
         pyr.dtype = ofb200.DTYPE_BF16 if pyramid_dtype == torch.bfloat16 else ofb200.DTYPE_F32
         n = h * w
         self._buffers = []
+        self._views: Optional[List[Tensor]] = None
         with torch.cuda.device(self._dev):
             for lvl in range(num_levels):
                 # the tcgen05 builder writes the row padding itself (zeros); the CUDA-core builder does not,
@@ -98,10 +101,6 @@ class CorrBlock:
                 buf = alloc(b * n * int(pyr.q_stride[lvl]), dtype=pyramid_dtype, device=self._dev)
                 self._buffers.append(buf)
                 pyr.base[lvl] = buf.data_ptr()
-                qs, pitch = int(pyr.q_stride[lvl]), int(pyr.row_pitch[lvl])
-                self.corr_pyramid.append(
-                    torch.as_strided(buf, (b * n, 1, int(pyr.lvl_h[lvl]), int(pyr.lvl_w[lvl])), (qs, qs, pitch, 1))
-                )
             self._pyr = pyr
             scale = 1.0 / math.sqrt(float(c))
             if builder == "tcgen05":
@@ -119,6 +118,29 @@ class CorrBlock:
                 ofb200.check(rc, "ofb_corr_pyramid_simt_f32")
             else:
                 raise ValueError(f"CorrBlock: unknown builder {builder!r}")
+
+    @property
+    def corr_pyramid(self) -> List[Tensor]:
+        """The levels with the reference's shapes (B*h*w, 1, h_l, w_l) (reference corr.py:48-54).
+
+        Row layout: strided views of the padded buffers.  8x4-blocked layout (tcgen05 builder): the
+        blocks are unfolded into a copy on first access -- the lookup never needs this, only callers
+        that inspect the volume do."""
+        if self._views is None:
+            b, _, h, w = self._shape
+            n = h * w
+            views = []
+            for lvl, buf in enumerate(self._buffers):
+                qs, pitch = int(self._pyr.q_stride[lvl]), int(self._pyr.row_pitch[lvl])
+                hl, wl = int(self._pyr.lvl_h[lvl]), int(self._pyr.lvl_w[lvl])
+                if self._pyr.layout == ofb200.LAYOUT_BLOCK8X4:
+                    blocks = buf.view(b * n, qs // (4 * pitch), pitch // 8, 4, 8)          # (q, by, bx, y, x)
+                    img = blocks.permute(0, 1, 3, 2, 4).reshape(b * n, qs // pitch, pitch)
+                    views.append(img[:, :hl, :wl].unsqueeze(1))
+                else:
+                    views.append(torch.as_strided(buf, (b * n, 1, hl, wl), (qs, qs, pitch, 1)))
+            self._views = views
+        return self._views
 
     def __call__(self, coords: Tensor, return_index: bool = False, out: Optional[Tensor] = None):
         """Index the pyramid (reference corr.py:56-77): coords (B, 2, h, w) -> (B, L*(2r+1)^2, h, w) fp32.
