@@ -69,7 +69,7 @@ def algorithmic(pairs):
         "lookup": {"launches": ITERS,
                    "bytes": ITERS * pairs * n * (LEVELS * (2 * RADIUS + 2) ** 2 * 2 + 8 + LEVELS * d2 * 4)},
         "convex_upsample": {"launches": 1, "bytes": pairs * n * 4 * (576 + 2 + 128)},
-        "warp": {"launches": 2, "bytes": pairs * H * W * (4 * (3 + 2 + 3) + 1 + 16)},   # + normalize: 16 B/px
+        "warp": {"launches": 1, "bytes": pairs * H * W * (4 * (3 + 2 + 3) + 1)},        # normalize fused
         "epe": {"launches": 1, "bytes": pairs * H * W * 20},
     }
 

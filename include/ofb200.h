@@ -62,11 +62,14 @@ int64_t ofb_launch_count(void);
  *   out   (B,C,H,W) fp32 NCHW
  *   valid_or_null (B,H,W) u8: 1 iff -1 < grid < 1 on both axes -- the predicate of
  *                 bilinear_sampler's mask (methods/raft/model/utils.py:76-78)
- *   variant: 0 = auto, 1 = direct gather, 2 = shared-memory staged neighbourhood
+ *   variant: 0 = auto, 1 = direct gather, 2 = shared-memory staged neighbourhood, 3 = row kernel
+ *   flow_mul_x/y: the flow is multiplied by these (one rounded fp32 multiply) before the grid is
+ *                 formed: 1, 1 for the reference's normalised flow; 2/max(W-1,1), 2/max(H-1,1) fuses
+ *                 optical_flow.normalize (operator.py:117-130) for pixel-unit flows, bit-identically
  * ------------------------------------------------------------------------------------- */
 int ofb_warp_f32(const float* frame, const float* flow, float* out, uint8_t* valid_or_null,
                  int B, int C, int H, int W, int mode, int padding_mode, int align_corners,
-                 int channels_last, int variant, void* stream);
+                 int channels_last, int variant, float flow_mul_x, float flow_mul_y, void* stream);
 
 /* warp_grid alone (operator.py:36-56): flow (B,H,W,2) -> grid (B,H,W,2). */
 int ofb_warp_grid_f32(const float* flow_bhw2, float* grid_bhw2, int B, int H, int W, void* stream);

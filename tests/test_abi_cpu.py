@@ -58,7 +58,7 @@ def test_pyramid_layout_is_host_only(lib):
 
 def test_argument_validation_without_launch(lib):
     null = None
-    assert lib.ofb_warp_f32(null, null, null, null, 1, 3, 8, 8, 0, 1, 0, 0, 0, null) == -1
+    assert lib.ofb_warp_f32(null, null, null, null, 1, 3, 8, 8, 0, 1, 0, 0, 0, 1.0, 1.0, null) == -1
     assert lib.ofb_convex_upsample_f32(null, null, null, 1, 4, 4, null) == -1
     assert lib.ofb_epe_reduce_f32(null, null, null, null, 1, 4, 4, null) == -1
     assert lib.ofb_corr_lookup(null, null, null, null, null, 1, 4, 4, 4, null) == -1

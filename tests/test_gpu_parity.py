@@ -61,7 +61,7 @@ def test_warp_reference_known_answers():
     assert torch.equal(warp(img, normalize(flow)), torch.tensor([[[2.0], [2.0]]]).unsqueeze(0))
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 def test_warp_golden(golden, variant):
     from optical_flow import normalize, warp
 
@@ -83,7 +83,7 @@ def test_warp_options_golden(golden, mode, pad, ac):
 
     g = golden("warp")
     ref = g[f"opt_{mode}_{pad}_{int(ac)}"]
-    for variant in ([1] if mode == "nearest" else [1, 2]):
+    for variant in ([1] if mode == "nearest" else [1, 2, 3]):
         out = N(warp(T(g["opt_frame"]), T(g["opt_flow"]), mode=mode, padding_mode=pad, align_corners=ac, variant=variant))
         if mode == "nearest":
             assert np.mean(out != ref) <= 0.005
@@ -103,12 +103,15 @@ def test_warp_vs_oracle(shape, sigma, pad, ac):
     flow = oracle.normalize(flow_px).astype(np.float32)
     ref, ref_mask = oracle.warp(frame, flow, padding_mode=pad, align_corners=ac, return_mask=True)
     outs = []
-    for variant in (1, 2):
+    for variant in (1, 2, 3):
         out, mask = warp(T(frame), T(flow), padding_mode=pad, align_corners=ac, return_mask=True, variant=variant)
         assert maxabs(N(out), ref) <= 1e-5, variant
         assert np.array_equal(N(mask).astype(np.uint8), ref_mask), variant      # validity mask bit-exact
         outs.append(N(out))
-    assert np.array_equal(outs[0], outs[1])                                      # both kernels agree bit for bit
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])  # all kernels agree bit for bit
+    # fused normalize: pixel-unit flow in, same bits out
+    fused, fmask = warp(T(frame), T(flow_px), padding_mode=pad, align_corners=ac, return_mask=True, pixel_flow=True)
+    assert np.array_equal(N(fused), outs[2]) and np.array_equal(N(fmask).astype(np.uint8), ref_mask)
     assert maxabs(N(normalize(T(flow_px))), flow) == 0.0
 
 
@@ -139,7 +142,8 @@ def test_warp_full_size_properties():
     flow = torch.randn((b, 2, h, w), device="cuda", generator=gen) * 0.01
     o1 = warp(frame, flow, variant=1)
     o2 = warp(frame, flow, variant=2)
-    assert torch.equal(o1, o2)
+    o3 = warp(frame, flow, variant=3)
+    assert torch.equal(o1, o2) and torch.equal(o1, o3)
     frame2 = torch.rand((b, c, h, w), device="cuda", generator=gen)
     lin = warp(frame + frame2, flow)
     assert float((lin - (o1 + warp(frame2, flow))).abs().max()) <= 4e-6

@@ -78,7 +78,7 @@ def bench_warp_c2(variants=(0,), flows=("white5px", "smooth5px"), masks=(1,)):
                     k[0] ^= 1
                     rc = lib.ofb_warp_f32(ofb200.ptr(frames[k[0]]), ofb200.ptr(flow), ofb200.ptr(out),
                                           ofb200.ptr(mask) if with_mask else None, b, c, h, w, 0, 1, 0, 0, variant,
-                                          ofb200.stream_ptr())
+                                          1.0, 1.0, ofb200.stream_ptr())
                     assert rc == 0
                 ms = timeit(run)
                 recs.append(record(f"C2 K1 warp 32x3x436x1024 variant={variant} flow={fname} mask={with_mask}", ms,

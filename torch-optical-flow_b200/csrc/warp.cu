@@ -15,6 +15,8 @@
 //     (global fallback for the rare tap outside the staged window).  HBM sees each frame
 //     line about once; the gather runs at shared-memory speed.
 // HBM roofline: 4*(C + 2 + C) bytes per pixel (+1 for the u8 mask).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -26,13 +28,31 @@ struct SrcPos {
     bool valid;
 };
 
+// flow multipliers: 1 for a normalised flow (the reference's contract); 2/(W-1), 2/(H-1) fuse
+// optical_flow.normalize (operator.py:117-130) into the warp -- one separately rounded multiply, as there
+struct FlowMul {
+    float x, y;
+};
+
+template <int PAD, bool AC>
+__device__ __forceinline__ SrcPos source_from_flow(float fx, float fy, int i, int j, int H, int W, float step_x,
+                                                   float step_y, FlowMul fm) {
+    const float gx = __fadd_rn(linspace_m1_p1(j, W, step_x), __fmul_rn(fx, fm.x));
+    const float gy = __fadd_rn(linspace_m1_p1(i, H, step_y), __fmul_rn(fy, fm.y));
+    SrcPos s;
+    s.ix = source_index<PAD, AC>(gx, W);
+    s.iy = source_index<PAD, AC>(gy, H);
+    s.valid = (gx > -1.0f) && (gy > -1.0f) && (gx < 1.0f) && (gy < 1.0f);
+    return s;
+}
+
 template <int PAD, bool AC>
 __device__ __forceinline__ SrcPos source_position(const float* __restrict__ flow, int b, int i, int j, int H, int W,
-                                                  float step_x, float step_y) {
+                                                  float step_x, float step_y, FlowMul fm = FlowMul{1.0f, 1.0f}) {
     const size_t HW = (size_t)H * W;
     const size_t p = (size_t)i * W + j;
-    float fx = __ldg(flow + ((size_t)b * 2 + 0) * HW + p);
-    float fy = __ldg(flow + ((size_t)b * 2 + 1) * HW + p);
+    float fx = __fmul_rn(__ldg(flow + ((size_t)b * 2 + 0) * HW + p), fm.x);
+    float fy = __fmul_rn(__ldg(flow + ((size_t)b * 2 + 1) * HW + p), fm.y);
     float gx = __fadd_rn(linspace_m1_p1(j, W, step_x), fx);
     float gy = __fadd_rn(linspace_m1_p1(i, H, step_y), fy);
     SrcPos s;
@@ -46,7 +66,7 @@ __device__ __forceinline__ SrcPos source_position(const float* __restrict__ flow
 template <int MODE, int PAD, bool AC, bool NHWC>
 __global__ void __launch_bounds__(256) warp_direct_kernel(const float* __restrict__ frame, const float* __restrict__ flow,
                                                           float* __restrict__ out, uint8_t* __restrict__ valid, int B,
-                                                          int C, int H, int W) {
+                                                          int C, int H, int W, FlowMul fm) {
     const size_t HW = (size_t)H * W;
     const size_t total = (size_t)B * HW;
     const float step_x = linspace_step(W), step_y = linspace_step(H);
@@ -54,7 +74,7 @@ __global__ void __launch_bounds__(256) warp_direct_kernel(const float* __restric
         const int b = (int)(q / HW);
         const size_t p = q - (size_t)b * HW;
         const int i = (int)(p / W), j = (int)(p - (size_t)i * W);
-        SrcPos s = source_position<PAD, AC>(flow, b, i, j, H, W, step_x, step_y);
+        SrcPos s = source_position<PAD, AC>(flow, b, i, j, H, W, step_x, step_y, fm);
         if (valid) valid[q] = s.valid ? 1 : 0;
         if (MODE == OFB_MODE_NEAREST) {
             int x = (int)rintf(s.ix), y = (int)rintf(s.iy);
@@ -137,7 +157,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 template <int PAD, bool AC>
 __global__ void __launch_bounds__(NT) warp_staged_kernel(const float* __restrict__ frame, const float* __restrict__ flow,
                                                          float* __restrict__ out, uint8_t* __restrict__ valid, int B,
-                                                         int C, int H, int W, int vec4) {
+                                                         int C, int H, int W, int vec4, FlowMul fm) {
     extern __shared__ __align__(16) float win[];  // [cg][WIN_H][pitch]
     __shared__ int s_box[4];                      // min x, max x, min y, max y of the taps
     const int b = blockIdx.z;
@@ -156,7 +176,7 @@ __global__ void __launch_bounds__(NT) warp_staged_kernel(const float* __restrict
         const int i = tile_y + ty + k * (NT / TW), j = tile_x + tx;
         ix[k] = 0.0f; iy[k] = 0.0f;
         if (i < H && j < W) {
-            SrcPos s = source_position<PAD, AC>(flow, b, i, j, H, W, step_x, step_y);
+            SrcPos s = source_position<PAD, AC>(flow, b, i, j, H, W, step_x, step_y, fm);
             ix[k] = s.ix; iy[k] = s.iy;
             if (valid) valid[(size_t)b * HW + (size_t)i * W + j] = s.valid ? 1 : 0;
             // clamp before the int conversion: zeros padding can leave coordinates far outside
@@ -246,6 +266,67 @@ __global__ void __launch_bounds__(NT) warp_staged_kernel(const float* __restrict
     }
 }
 
+// ------------------------------------------------------------------------------ row kernel
+// The default NCHW bilinear path.  grid = (column groups, row groups, batch): no per-pixel integer division,
+// 32-bit in-plane offsets.  Lane <-> column (every load / store of a warp is one or two 128-byte lines), and a
+// thread walks RPT consecutive rows of its column: the lower taps of row i are the upper taps of row i+1 for
+// smooth flows, so they hit L1.  The coordinate pipeline and the 4 tap offsets are computed once per pixel
+// and reused for every channel.
+constexpr int RPT_DEFAULT = 4;   // rows per thread
+
+template <int PAD, bool AC, int RPT>
+__global__ void __launch_bounds__(128) warp_rows_kernel(const float* __restrict__ frame, const float* __restrict__ flow,
+                                                        float* __restrict__ out, uint8_t* __restrict__ valid, int C,
+                                                        int H, int W, FlowMul fm) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.z;
+    const int i0 = blockIdx.y * RPT;
+    if (j >= W) return;
+    const int HW = H * W;                                     // launch guard: H*W < 2^30
+    const float step_x = linspace_step(W), step_y = linspace_step(H);
+    const float* fxp = flow + (size_t)(b * 2) * HW;
+    const float* fyp = fxp + HW;
+    int o00[RPT];
+    float w00[RPT], w01[RPT], w10[RPT], w11[RPT];
+    unsigned inb = 0;
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+        const int i = i0 + k;
+        o00[k] = 0; w00[k] = w01[k] = w10[k] = w11[k] = 0.0f;
+        if (i >= H) continue;
+        const int off = i * W + j;
+        const SrcPos s = source_from_flow<PAD, AC>(__ldg(fxp + off), __ldg(fyp + off), i, j, H, W, step_x, step_y, fm);
+        if (valid) valid[(size_t)b * HW + off] = s.valid ? 1 : 0;
+        const float x0f = floorf(s.ix), y0f = floorf(s.iy);
+        const float wx1 = s.ix - x0f, wx0 = (x0f + 1.0f) - s.ix;
+        const float wy1 = s.iy - y0f, wy0 = (y0f + 1.0f) - s.iy;
+        w00[k] = wx0 * wy0; w01[k] = wx1 * wy0; w10[k] = wx0 * wy1; w11[k] = wx1 * wy1;
+        // clamp before the int conversion: zeros padding can leave coordinates far outside; NaN samples nothing
+        const int x0 = (int)fminf(fmaxf(x0f, -2.0f), (float)W + 1.0f), y0 = (int)fminf(fmaxf(y0f, -2.0f), (float)H + 1.0f);
+        const bool fin = x0f == x0f && y0f == y0f;
+        const bool inx0 = fin && x0 >= 0 && x0 < W, inx1 = fin && x0 + 1 >= 0 && x0 + 1 < W;
+        const bool iny0 = y0 >= 0 && y0 < H, iny1 = y0 + 1 >= 0 && y0 + 1 < H;
+        inb |= (((iny0 && inx0) ? 1u : 0u) | ((iny0 && inx1) ? 2u : 0u) | ((iny1 && inx0) ? 4u : 0u) |
+                ((iny1 && inx1) ? 8u : 0u)) << (4 * k);
+        o00[k] = y0 * W + x0;
+    }
+    for (int c = 0; c < C; ++c) {
+        const float* plane = frame + (size_t)(b * C + c) * HW;
+        float* op = out + (size_t)(b * C + c) * HW + i0 * W + j;
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            if (i0 + k >= H) continue;
+            const unsigned m = inb >> (4 * k);
+            const float* p = plane + o00[k];
+            float acc = 0.0f;
+            if (m & 1u) acc = __fmaf_rn(__ldg(p), w00[k], acc);
+            if (m & 2u) acc = __fmaf_rn(__ldg(p + 1), w01[k], acc);
+            if (m & 4u) acc = __fmaf_rn(__ldg(p + W), w10[k], acc);
+            if (m & 8u) acc = __fmaf_rn(__ldg(p + W + 1), w11[k], acc);
+            op[k * W] = acc;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) warp_grid_kernel(const float* __restrict__ flow, float* __restrict__ grid, int B,
                                                         int H, int W) {
     const size_t total = (size_t)B * H * W;
@@ -262,22 +343,39 @@ __global__ void __launch_bounds__(256) warp_grid_kernel(const float* __restrict_
 
 template <int MODE, int PAD, bool AC>
 int launch_direct(const float* frame, const float* flow, float* out, uint8_t* valid, int B, int C, int H, int W,
-                  int channels_last, cudaStream_t st) {
+                  int channels_last, FlowMul fm, cudaStream_t st) {
     const size_t total = (size_t)B * H * W;
     int blocks = (int)((total + 255) / 256);
     const int cap = ofb_num_sms() * 32;
     if (blocks > cap) blocks = cap;
     if (channels_last)
-        warp_direct_kernel<MODE, PAD, AC, true><<<blocks, 256, 0, st>>>(frame, flow, out, valid, B, C, H, W);
+        warp_direct_kernel<MODE, PAD, AC, true><<<blocks, 256, 0, st>>>(frame, flow, out, valid, B, C, H, W, fm);
     else
-        warp_direct_kernel<MODE, PAD, AC, false><<<blocks, 256, 0, st>>>(frame, flow, out, valid, B, C, H, W);
+        warp_direct_kernel<MODE, PAD, AC, false><<<blocks, 256, 0, st>>>(frame, flow, out, valid, B, C, H, W, fm);
+    OFB_LAUNCH_CHECK();
+    return OFB_OK;
+}
+
+template <int PAD, bool AC>
+int launch_rows(const float* frame, const float* flow, float* out, uint8_t* valid, int B, int C, int H, int W,
+                FlowMul fm, cudaStream_t st) {
+    static int rpt = 0;
+    if (!rpt) {
+        const char* e = getenv("OFB_WARP_RPT");           // tuning override
+        rpt = e ? atoi(e) : RPT_DEFAULT;
+        if (rpt != 2 && rpt != 4 && rpt != 8) rpt = RPT_DEFAULT;
+    }
+    dim3 grid((W + 127) / 128, (H + rpt - 1) / rpt, B);
+    if (rpt == 2) warp_rows_kernel<PAD, AC, 2><<<grid, 128, 0, st>>>(frame, flow, out, valid, C, H, W, fm);
+    else if (rpt == 8) warp_rows_kernel<PAD, AC, 8><<<grid, 128, 0, st>>>(frame, flow, out, valid, C, H, W, fm);
+    else warp_rows_kernel<PAD, AC, 4><<<grid, 128, 0, st>>>(frame, flow, out, valid, C, H, W, fm);
     OFB_LAUNCH_CHECK();
     return OFB_OK;
 }
 
 template <int PAD, bool AC>
 int launch_staged(const float* frame, const float* flow, float* out, uint8_t* valid, int B, int C, int H, int W,
-                  cudaStream_t st) {
+                  FlowMul fm, cudaStream_t st) {
     const int cg = C < CG_MAX ? C : CG_MAX;
     const size_t smem = (size_t)cg * WIN_H * WIN_W * sizeof(float);
     static bool configured = false;
@@ -288,17 +386,17 @@ int launch_staged(const float* frame, const float* flow, float* out, uint8_t* va
     }
     const int vec4 = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(frame) & 15) == 0);
     dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, B);
-    warp_staged_kernel<PAD, AC><<<grid, NT, smem, st>>>(frame, flow, out, valid, B, C, H, W, vec4);
+    warp_staged_kernel<PAD, AC><<<grid, NT, smem, st>>>(frame, flow, out, valid, B, C, H, W, vec4, fm);
     OFB_LAUNCH_CHECK();
     return OFB_OK;
 }
 
 template <int MODE>
 int dispatch_direct(int pad, int ac, const float* frame, const float* flow, float* out, uint8_t* valid, int B, int C,
-                    int H, int W, int cl, cudaStream_t st) {
+                    int H, int W, int cl, FlowMul fm, cudaStream_t st) {
 #define OFB_CASE(P, A)                                                                                 \
     if (pad == P && ac == (A ? 1 : 0))                                                                  \
-        return launch_direct<MODE, P, A>(frame, flow, out, valid, B, C, H, W, cl, st);
+        return launch_direct<MODE, P, A>(frame, flow, out, valid, B, C, H, W, cl, fm, st);
     OFB_CASE(OFB_PAD_ZEROS, false)
     OFB_CASE(OFB_PAD_ZEROS, true)
     OFB_CASE(OFB_PAD_BORDER, false)
@@ -309,10 +407,12 @@ int dispatch_direct(int pad, int ac, const float* frame, const float* flow, floa
     return OFB_EINVAL;
 }
 
-int dispatch_staged(int pad, int ac, const float* frame, const float* flow, float* out, uint8_t* valid, int B, int C,
-                    int H, int W, cudaStream_t st) {
-#define OFB_CASE(P, A) \
-    if (pad == P && ac == (A ? 1 : 0)) return launch_staged<P, A>(frame, flow, out, valid, B, C, H, W, st);
+int dispatch_staged(int pad, int ac, int rows, const float* frame, const float* flow, float* out, uint8_t* valid, int B,
+                    int C, int H, int W, FlowMul fm, cudaStream_t st) {
+#define OFB_CASE(P, A)                                                                                   \
+    if (pad == P && ac == (A ? 1 : 0))                                                                    \
+        return rows ? launch_rows<P, A>(frame, flow, out, valid, B, C, H, W, fm, st)                      \
+                    : launch_staged<P, A>(frame, flow, out, valid, B, C, H, W, fm, st);
     OFB_CASE(OFB_PAD_ZEROS, false)
     OFB_CASE(OFB_PAD_ZEROS, true)
     OFB_CASE(OFB_PAD_BORDER, false)
@@ -327,22 +427,26 @@ int dispatch_staged(int pad, int ac, const float* frame, const float* flow, floa
 
 OFB_API int ofb_warp_f32(const float* frame, const float* flow, float* out, uint8_t* valid_or_null, int B, int C, int H,
                          int W, int mode, int padding_mode, int align_corners, int channels_last, int variant,
-                         void* stream) {
+                         float flow_mul_x, float flow_mul_y, void* stream) {
     if (!frame || !flow || !out || B < 0 || C < 0 || H < 0 || W < 0) return OFB_EINVAL;
     if (mode != OFB_MODE_BILINEAR && mode != OFB_MODE_NEAREST) return OFB_EINVAL;
-    if (padding_mode < 0 || padding_mode > 2 || variant < 0 || variant > 2) return OFB_EINVAL;
+    if (padding_mode < 0 || padding_mode > 2 || variant < 0 || variant > 3) return OFB_EINVAL;
     if ((size_t)B * C * H * W == 0) return OFB_OK;
     if (B > 65535) return OFB_EUNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
-    const bool can_stage = mode == OFB_MODE_BILINEAR && !channels_last;
-    if (variant == 2 && !can_stage) return OFB_EUNSUPPORTED;
-    const bool staged = variant == 2 || (variant == 0 && can_stage && H >= TH && W >= TW);
-    if (staged) return dispatch_staged(padding_mode, align_corners, frame, flow, out, valid_or_null, B, C, H, W, st);
+    const FlowMul fm{flow_mul_x, flow_mul_y};
+    const bool nchw_bilinear = mode == OFB_MODE_BILINEAR && !channels_last;
+    const bool can_rows = nchw_bilinear && H <= 65535 * 2 && (long long)H * W < (1LL << 30) && (long long)B * C * H * W < (1LL << 40);
+    if ((variant == 2 && !nchw_bilinear) || (variant == 3 && !can_rows)) return OFB_EUNSUPPORTED;
+    // auto: the row kernel; 1 = direct gather (also nearest / NHWC), 2 = shared-memory staged, 3 = row kernel
+    const int v = variant != 0 ? variant : (can_rows ? 3 : 1);
+    if (v == 2 || v == 3)
+        return dispatch_staged(padding_mode, align_corners, v == 3, frame, flow, out, valid_or_null, B, C, H, W, fm, st);
     if (mode == OFB_MODE_BILINEAR)
         return dispatch_direct<OFB_MODE_BILINEAR>(padding_mode, align_corners, frame, flow, out, valid_or_null, B, C, H,
-                                                  W, channels_last, st);
+                                                  W, channels_last, fm, st);
     return dispatch_direct<OFB_MODE_NEAREST>(padding_mode, align_corners, frame, flow, out, valid_or_null, B, C, H, W,
-                                             channels_last, st);
+                                             channels_last, fm, st);
 }
 
 OFB_API int ofb_warp_grid_f32(const float* flow_bhw2, float* grid_bhw2, int B, int H, int W, void* stream) {

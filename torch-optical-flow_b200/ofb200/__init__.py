@@ -48,7 +48,7 @@ SIGNATURES = {
     "ofb_version": (_i, []),
     "ofb_strerror": (ctypes.c_char_p, [_i]),
     "ofb_launch_count": (_i64, []),
-    "ofb_warp_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "ofb_warp_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp]),
     "ofb_warp_grid_f32": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "ofb_scale_flow_f32": (_i, [_vp, _vp, _i, _i64, _f, _f, _vp]),
     "ofb_resize_bilinear_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp]),

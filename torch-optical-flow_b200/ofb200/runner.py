@@ -8,7 +8,7 @@ methods/raft/model/raft.py:112-142) followed by the library operators and metric
     CorrBlock(fmap1, fmap2)                    K2  prep x3 + tcgen05 pyramid x2 (levels 0-1, levels 2-3)
     corr_fn(coords) x iters                    K3  one launch per refinement iteration
     RAFT.upsample_flow(flow_lo, up_mask)       K4b convex 8x upsampling
-    warp(frame, normalize(flow_up)) + mask     scale + K1
+    warp(frame, normalize(flow_up)) + mask     K1 (normalize fused: pixel_flow=True)
     AverageEndPointError.update(flow_up, gt)   K4c masked sum / count
 
 The GRU update block between the lookups is out of scope, so its products
@@ -22,7 +22,7 @@ from torch import Tensor
 from model.corr import CorrBlock
 from model.raft import upsample_flow
 from optical_flow.metrics.epe import AverageEndPointError
-from optical_flow.operator.operator import normalize, warp
+from optical_flow.operator.operator import warp
 
 FIELDS = ("fmap1", "fmap2", "coords", "flow_lo", "up_mask", "frame", "target", "valid")
 
@@ -83,14 +83,14 @@ def hot_path(batch: Dict[str, Tensor], metric: AverageEndPointError, timers: Opt
             corr = blk(batch["coords"][it], out=lookup_out)
     with sp("convex_upsample", 1):
         flow_up = upsample_flow(batch["flow_lo"], batch["up_mask"])
-    with sp("warp", 2):
-        warped, vmask = warp(batch["frame"], normalize(flow_up), return_mask=True)
+    with sp("warp", 1):
+        warped, vmask = warp(batch["frame"], flow_up, return_mask=True, pixel_flow=True)   # normalize fused
     with sp("epe", 1):
         metric.update(flow_up, batch["target"], batch["valid"])
     return {"corr": corr, "flow_up": flow_up, "warped": warped, "mask": vmask}
 
 
-LAUNCHES_PER_PASS = lambda iters: 5 + iters + 1 + 2 + 1  # noqa: E731  (prep x3, pyramid x2, lookups, upsample, scale, warp, epe)
+LAUNCHES_PER_PASS = lambda iters: 5 + iters + 1 + 1 + 1  # noqa: E731  (prep x3, pyramid x2, lookups, upsample, warp, epe)
 
 
 class HostStagedRunner:

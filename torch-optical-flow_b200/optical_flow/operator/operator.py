@@ -37,6 +37,7 @@ def warp(
     align_corners: bool = False,
     return_mask: bool = False,
     variant: int = 0,
+    pixel_flow: bool = False,
 ) -> Union[Tensor, Tuple[Tensor, Tensor]]:
     """Inverse warping with optical flow (reference operator.py:8-33).
 
@@ -49,7 +50,9 @@ def warp(
         return_mask: extension (default off): also return the (B, H, W) bool validity mask -- the
             predicate of ``bilinear_sampler(mask=True)`` (reference methods/raft/model/utils.py:76-78)
             evaluated on the warp grid: True where the source position lies strictly inside the frame
-        variant: kernel selection, 0 = auto, 1 = direct gather, 2 = shared-memory staged
+        variant: kernel selection, 0 = auto, 1 = direct gather, 2 = shared-memory staged, 3 = row kernel
+        pixel_flow: extension (default off): `flow` is in pixel units and :func:`normalize` is fused into
+            the kernel -- ``warp(f, flow, pixel_flow=True)`` equals ``warp(f, normalize(flow))`` bit for bit
 
     Returns:
         The warped image (B, C, H, W), contiguous; with ``return_mask`` a tuple (warped, mask).
@@ -66,6 +69,7 @@ def warp(
     if tuple(flow.shape) != (b, 2, h, w):
         raise RuntimeError(f"warp: flow shape {tuple(flow.shape)} does not match frame {tuple(frame.shape)}")
     _check_f32(frame, flow)
+    mul_x, mul_y = (2.0 / max(w - 1, 1), 2.0 / max(h - 1, 1)) if pixel_flow else (1.0, 1.0)
 
     def run(frame_d: Tensor, flow_d: Tensor):
         lib = ofb200.load()
@@ -80,7 +84,7 @@ def warp(
         rc = lib.ofb_warp_f32(
             ofb200.ptr(frame_d), ofb200.ptr(flow_d), ofb200.ptr(out), ofb200.ptr(mask), b, c, h, w,
             ofb200.MODE[mode], ofb200.PAD[padding_mode], int(bool(align_corners)), int(channels_last),
-            int(variant), ofb200.stream_ptr(),
+            int(variant), mul_x, mul_y, ofb200.stream_ptr(),
         )
         ofb200.check(rc, "ofb_warp_f32")
         return (out, mask.bool()) if return_mask else out
