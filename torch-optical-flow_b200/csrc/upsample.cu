@@ -44,25 +44,35 @@ __global__ void __launch_bounds__(NT) convex_upsample_kernel(const float* __rest
 
     const float* mp = mask + (size_t)n * 576 * hw + (size_t)(i * 8) * hw + p;
     float ox[8], oy[8];
+    // JG sub-columns at a time: 9*JG independent 128-byte-coalesced loads are in flight per warp before
+    // the first softmax starts (the kernel is a pure stream of the 576-channel mask: latency, not math)
+    constexpr int JG = 4;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        float m[9];
+    for (int jg = 0; jg < 8; jg += JG) {
+        float m[JG][9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) m[k] = __ldg(mp + (size_t)(k * 64 + j) * hw);
-        float mx = m[0];
+        for (int jj = 0; jj < JG; ++jj)
 #pragma unroll
-        for (int k = 1; k < 9; ++k) mx = fmaxf(mx, m[k]);
-        float s = 0.0f;
+            for (int k = 0; k < 9; ++k) m[jj][k] = __ldg(mp + (size_t)(k * 64 + jg + jj) * hw);
 #pragma unroll
-        for (int k = 0; k < 9; ++k) { m[k] = expf(m[k] - mx); s += m[k]; }
-        float ax = 0.0f, ay = 0.0f;
+        for (int jj = 0; jj < JG; ++jj) {
+            float mx = m[jj][0];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) {
-            const float wk = __fdiv_rn(m[k], s);
-            ax = __fmaf_rn(wk, nbx[k], ax);
-            ay = __fmaf_rn(wk, nby[k], ay);
+            for (int k = 1; k < 9; ++k) mx = fmaxf(mx, m[jj][k]);
+            float s = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { m[jj][k] = expf(m[jj][k] - mx); s += m[jj][k]; }
+            // softmax-weighted sums, normalised once at the end: sum_k e_k v_k / sum_k e_k (one division per
+            // component instead of nine; differs from the reference's per-weight division by <= 2 ulp)
+            float ax = 0.0f, ay = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) {
+                ax = __fmaf_rn(m[jj][k], nbx[k], ax);
+                ay = __fmaf_rn(m[jj][k], nby[k], ay);
+            }
+            const float inv = __fdiv_rn(1.0f, s);
+            ox[jg + jj] = ax * inv; oy[jg + jj] = ay * inv;
         }
-        ox[j] = ax; oy[j] = ay;
     }
     const size_t W8 = (size_t)8 * w, H8 = (size_t)8 * h;
     float* dx = out + ((size_t)n * 2 + 0) * H8 * W8 + (size_t)(8 * y + i) * W8 + 8 * x;
