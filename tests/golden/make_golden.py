@@ -205,8 +205,57 @@ def make_upsample_epe():
     save("upsample_epe", ref_call="RAFT.upsample_flow; optical_flow.metrics.epe.end_point_error / AverageEndPointError", **cases)
 
 
+# ------------------------------------------------------ RAFT.forward trace (raft.py:87-147)
+def make_raft_trace():
+    """Run the UNMODIFIED reference RAFT (random weights, eval mode) on one small image pair and record
+    every tensor that crosses the hot-path boundary inside forward(): the feature maps handed to
+    CorrBlock (raft.py:112), the coordinates and result of each corr_fn call (raft.py:128), the inputs
+    and result of each upsample_flow call (raft.py:140).  The GPU test replays those calls on the B200
+    kernels (section 8f, row 1: the accelerated block inside the unmodified model)."""
+    import model.raft as raft_mod
+
+    torch.manual_seed(1234)
+    net = RAFT()
+    net.eval()
+    rec = {"coords": [], "corr": [], "up_flow": [], "up_mask": [], "up_out": []}
+
+    class Recorder(corr_mod.CorrBlock):
+        def __init__(self, fmap1, fmap2, num_levels=4, radius=4):
+            rec["fmap1"], rec["fmap2"] = fmap1.clone(), fmap2.clone()
+            super().__init__(fmap1, fmap2, num_levels=num_levels, radius=radius)
+
+        def __call__(self, coords):
+            out = super().__call__(coords)
+            rec["coords"].append(coords.clone())
+            rec["corr"].append(out.clone())
+            return out
+
+    orig_up = RAFT.upsample_flow
+
+    def up(flow, mask):
+        out = orig_up(flow, mask)
+        rec["up_flow"].append(flow.clone()); rec["up_mask"].append(mask.clone()); rec["up_out"].append(out.clone())
+        return out
+
+    raft_mod.CorrBlock = Recorder
+    net.upsample_flow = up
+    img0 = 255.0 * torch.rand(1, 3, 128, 192, generator=g(70))   # 16x24 features: level 3 is 2x3 (1x1 would divide by zero, utils.py:70)
+    img1 = torch.roll(img0, shifts=(2, -3), dims=(2, 3)) + 4.0 * torch.randn(1, 3, 128, 192, generator=g(71))
+    with torch.no_grad():
+        flow_lo, flow_up = net(img0, img1, iters=2, test_mode=True)
+    raft_mod.CorrBlock = corr_mod.CorrBlock
+    save("raft_trace", ref_call="RAFT()(img0, img1, iters=2, test_mode=True), hooks on CorrBlock / upsample_flow",
+         fmap1=rec["fmap1"], fmap2=rec["fmap2"], coords=torch.stack(rec["coords"]), corr=torch.stack(rec["corr"]),
+         up_flow=torch.stack(rec["up_flow"]), up_mask=torch.stack(rec["up_mask"]), up_out=torch.stack(rec["up_out"]),
+         flow_lo=flow_lo, flow_up=flow_up)
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["raft_trace"]:
+        make_raft_trace()
+        sys.exit(0)
     make_warp()
     make_resize()
     make_corr()
     make_upsample_epe()
+    make_raft_trace()

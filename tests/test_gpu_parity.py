@@ -595,3 +595,31 @@ def test_corr_pyramid_full_size_properties():
     v = blk.corr_pyramid[0].view(b, h * w, h, w)[bsel].reshape(h * w, h * w).float()
     vt = blk_t.corr_pyramid[0].view(b, h * w, h, w)[bsel].reshape(h * w, h * w).float()
     assert float((v - vt.t()).abs().max()) <= 0.05
+
+
+# =============================================================================== RAFT.forward trace
+@pytest.mark.parametrize("mode", ["fp32_simt", "bf16_tcgen05"])
+def test_raft_forward_trace(golden, mode):
+    """the accelerated block inside the unmodified model.  The reference's RAFT.forward was
+    run on CPU with hooks on the hot-path boundary (tests/golden/make_golden.py:make_raft_trace); here the
+    recorded CorrBlock / corr_fn / upsample_flow calls are replayed on the B200 kernels."""
+    from model.corr import CorrBlock
+    from model.raft import RAFT
+
+    g = golden("raft_trace")
+    f1, f2 = T(g["fmap1"]), T(g["fmap2"])
+    if mode == "fp32_simt":
+        blk, rtol = CorrBlock(f1, f2, radius=4, pyramid_dtype=torch.float32), 2e-4
+    else:
+        blk, rtol = CorrBlock(f1, f2, radius=4), 6e-3        # bf16 operands and bf16 stored volume
+        assert blk.builder == "tcgen05"
+    for it in range(g["coords"].shape[0]):
+        out = N(blk(T(g["coords"][it])))
+        ref = g["corr"][it]
+        assert out.shape == ref.shape
+        if mode == "fp32_simt":
+            assert maxabs(out, ref) <= rtol * max(1.0, float(np.abs(ref).max())), it
+        else:
+            assert np.linalg.norm(out - ref) / np.linalg.norm(ref) <= rtol, it
+        up = N(RAFT.upsample_flow(T(g["up_flow"][it]), T(g["up_mask"][it])))
+        assert maxabs(up, g["up_out"][it]) <= tol(g["up_out"][it]), it

@@ -524,13 +524,18 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         // (partial sectors measured a 2x slowdown of the whole kernel at w = 156)
                         const bool in_img = y < P.la.h && x < P.la.pitch;
                         const long long off_yx = piece_offset(P.la, y, x);
+                        // all 8 shared loads first, then the 8 global stores: the stores do not wait on each other's data
+                        uint4 val[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const int r = j * 4 + ra_q;
-                            const uint4 val = ld_shared_v4(stg_a + (uint32_t)r * 128u + (uint32_t)((ra_p ^ (r & 7)) << 4));
-                            if (in_img && qrow0 + r < P.Nq) {
-                                st_global_v4(P.la.base + (qglob0 + r) * P.la.q_stride + off_yx, val);
-                            }
+                            val[j] = ld_shared_v4(stg_a + (uint32_t)r * 128u + (uint32_t)((ra_p ^ (r & 7)) << 4));
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int r = j * 4 + ra_q;
+                            if (in_img && qrow0 + r < P.Nq)
+                                st_global_v4(P.la.base + (qglob0 + r) * P.la.q_stride + off_yx, val[j]);
                         }
                     }
                     if (P.has_b && !(PROF && (dbg & 2))) {

@@ -15,44 +15,59 @@
 namespace {
 
 // ---------------------------------------------------------------- cast + transpose
-constexpr int TP = 32;  // pixels per tile
-constexpr int TC = 64;  // channels per tile
+constexpr int TP = 32;    // pixels per tile
+constexpr int TCMAX = 256;  // channels per tile (the whole K extent of the tensor-core path)
 
+// One CTA turns a 32-pixel x C-channel tile: reads are 128-byte lines (32 pixels of one channel), 8 in
+// flight per thread; writes are whole 2*C-byte pixel rows of the K-major operand.
 template <int POOL>
 __global__ void __launch_bounds__(256) prep_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int C,
                                                    int h, int w, float scale) {
     // output pixel p = (yo, xo) of the (h/POOL) x (w/POOL) image = mean of a complete POOL x POOL block
-    __shared__ float tile[TC][TP + 1];
+    extern __shared__ float tile[];                       // [Ct][TP + 1]
     const int ho = h / POOL, wo = w / POOL, HWo = ho * wo, HW = h * w;
-    const int b = blockIdx.z, p0 = blockIdx.x * TP, c0 = blockIdx.y * TC;
+    const int b = blockIdx.z, p0 = blockIdx.x * TP, c0 = blockIdx.y * TCMAX;
+    const int Ct = min(TCMAX, C - c0);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // read: 64 channel rows x 32 pixels (POOL = 1: each row segment one 128-byte line)
     const int p = p0 + lane;
     const int yo = p / wo, xo = p - yo * wo;
-    for (int c = warp; c < TC; c += 8) {
-        const int cc = c0 + c;
-        float v = 0.0f;
-        if (cc < C && p < HWo) {
-            const float* src = in + ((size_t)b * C + cc) * HW + (size_t)(yo * POOL) * w + xo * POOL;
-            if (POOL == 1) {
-                v = __ldg(src);
-            } else {
+    const float* src0 = in + ((size_t)b * C + c0) * HW + (size_t)(yo * POOL) * w + xo * POOL;
+    const bool pok = p < HWo;
+    for (int cb = warp; cb < Ct; cb += 64) {              // 8 warps x 8 independent channel rows per pass
+        float v[8];
 #pragma unroll
-                for (int dy = 0; dy < POOL; ++dy)
+        for (int u = 0; u < 8; ++u) {
+            const int c = cb + 8 * u;
+            v[u] = 0.0f;
+            if (pok && c < Ct) {
+                const float* src = src0 + (size_t)c * HW;
+                if (POOL == 1) {
+                    v[u] = __ldg(src);
+                } else {
+                    float a = 0.0f;
 #pragma unroll
-                    for (int dx = 0; dx < POOL; ++dx) v += __ldg(src + dy * w + dx);
-                v *= 1.0f / (float)(POOL * POOL);
+                    for (int dy = 0; dy < POOL; ++dy)
+#pragma unroll
+                        for (int dx = 0; dx < POOL; ++dx) a += __ldg(src + dy * w + dx);
+                    v[u] = a * (1.0f / (float)(POOL * POOL));
+                }
             }
         }
-        tile[c][lane] = v * scale;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int c = cb + 8 * u;
+            if (c < Ct) tile[c * (TP + 1) + lane] = v[u] * scale;
+        }
     }
     __syncthreads();
-    // write: per pixel 64 channels = 128 bytes, one bf16x2 per lane
+    // write: one pixel row (Ct channels) per warp pass, bf16x2 per lane, 128 bytes per instruction
     for (int q = warp; q < TP; q += 8) {
-        const int pp = p0 + q, cc = c0 + 2 * lane;
-        if (pp < HWo && cc < C) {
-            __nv_bfloat162 v = __floats2bfloat162_rn(tile[2 * lane][q], tile[2 * lane + 1][q]);
-            *reinterpret_cast<__nv_bfloat162*>(out + ((size_t)b * HWo + pp) * C + cc) = v;
+        const int pp = p0 + q;
+        if (pp >= HWo) break;
+        __nv_bfloat16* dst = out + ((size_t)b * HWo + pp) * C + c0;
+        for (int cc = 2 * lane; cc < Ct; cc += 64) {
+            __nv_bfloat162 v2 = __floats2bfloat162_rn(tile[cc * (TP + 1) + q], tile[(cc + 1) * (TP + 1) + q]);
+            *reinterpret_cast<__nv_bfloat162*>(dst + cc) = v2;
         }
     }
 }
@@ -155,10 +170,11 @@ OFB_API int ofb_corr_prep_bf16(const float* fmap_nchw, void* out_km_bf16, int B,
     const int HWo = (h / pool) * (w / pool);
     if (B == 0 || HWo == 0) return OFB_OK;
     if (B > 65535) return OFB_EUNSUPPORTED;
-    dim3 grid((HWo + TP - 1) / TP, (C + TC - 1) / TC, B);
+    dim3 grid((HWo + TP - 1) / TP, (C + TCMAX - 1) / TCMAX, B);
+    const size_t smem = (size_t)(C < TCMAX ? C : TCMAX) * (TP + 1) * sizeof(float);      // <= 33 KiB
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(out_km_bf16);
-    if (pool == 1) prep_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(fmap_nchw, out, C, h, w, scale);
-    else prep_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(fmap_nchw, out, C, h, w, scale);
+    if (pool == 1) prep_kernel<1><<<grid, 256, smem, (cudaStream_t)stream>>>(fmap_nchw, out, C, h, w, scale);
+    else prep_kernel<4><<<grid, 256, smem, (cudaStream_t)stream>>>(fmap_nchw, out, C, h, w, scale);
     OFB_LAUNCH_CHECK();
     return OFB_OK;
 }
