@@ -297,7 +297,9 @@ __global__ void __launch_bounds__(128) lookup_tile_kernel(const LookupParams P, 
     const unsigned q1 = (unsigned)(s >> 1) & 1u, q2 = (unsigned)(s >> 2) & 1u, hs = (unsigned)(s & 1) * 16u;
     const bool ck0 = xa >= 0 && xa + 8 <= pitch;
     const bool ck1 = xa + 8 >= 0 && xa + 16 <= pitch;
-    const bool ck2 = (s + WIN > 16) && xa + 16 >= 0 && xa + 24 <= pitch;
+    // the last window column / row only carries weight when some tap slid by one (dmask != 0)
+    const int wcols = tx.dmask ? WIN : WIN - 1, wrows = ty.dmask ? WIN : WIN - 1;
+    const bool ck2 = (s + wcols > 16) && xa + 16 >= 0 && xa + 24 <= pitch;
     const __nv_bfloat16* slice = reinterpret_cast<const __nv_bfloat16*>(P.base[l]) + q * P.q_stride[l];
     float* outp = out + (b * (long long)(P.levels * DD) + (long long)l * DD) * HW + p;
 
@@ -307,26 +309,42 @@ __global__ void __launch_bounds__(128) lookup_tile_kernel(const LookupParams P, 
 #pragma unroll
         for (int i = 0; i < D; ++i) acc[k][i] = 0.0f;
 
-    uint4 c0v, c1v;
-    uint2 c2v;
-    auto load_row = [&](int r) {
-        const int y = ys + r;
-        const bool rok = !dead && y >= 0 && y < Hl;
-        // an aligned 8-element chunk is one row of an 8x4 block (blocked) or 8 consecutive row elements
-        const __nv_bfloat16* row = P.blocked
-            ? slice + ((long long)(y >> 2) * (pitch >> 3) + (xa >> 3)) * 32 + (y & 3) * 8
-            : slice + (long long)y * pitch + xa;
+    // Window rows -> this thread's private shared-memory slots with cp.async (16 bytes each, zero-filled when
+    // the chunk is outside the slice): every load of the window is in flight at once and none of them holds a
+    // register.  Slot (row r, chunk c) of thread t lives at ((r*3 + c) * blockDim + t) * 16: a warp's accesses
+    // are 512 contiguous bytes, conflict-free.
+    extern __shared__ __align__(16) uint8_t win_smem[];
+    const uint32_t my_slot = (uint32_t)__cvta_generic_to_shared(win_smem) + threadIdx.x * 16u;
+    const uint32_t slot_stride = blockDim.x * 16u;
+    {
         const int cstep = P.blocked ? 32 : 8;
-        c0v = make_uint4(0, 0, 0, 0); c1v = make_uint4(0, 0, 0, 0); c2v = make_uint2(0, 0);
-        if (rok && ck0) c0v = __ldg(reinterpret_cast<const uint4*>(row));
-        if (rok && ck1) c1v = __ldg(reinterpret_cast<const uint4*>(row + cstep));
-        if (rok && ck2) c2v = __ldg(reinterpret_cast<const uint2*>(row + 2 * cstep));
-    };
-    load_row(0);
+#pragma unroll
+        for (int r = 0; r < WIN; ++r) {
+            const int y = ys + r;
+            const bool rok = !dead && r < wrows && y >= 0 && y < Hl;
+            // an aligned 8-element chunk is one row of an 8x4 block (blocked) or 8 consecutive row elements
+            const __nv_bfloat16* row = P.blocked
+                ? slice + ((long long)(y >> 2) * (pitch >> 3) + (xa >> 3)) * 32 + (y & 3) * 8
+                : slice + (long long)y * pitch + xa;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const bool ok = rok && (c == 0 ? ck0 : c == 1 ? ck1 : ck2);
+                const void* src = ok ? (const void*)(row + c * cstep) : (const void*)slice;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(my_slot + (uint32_t)(r * 3 + c) * slot_stride),
+                             "l"(src), "r"(ok ? 16 : 0) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
 #pragma unroll
     for (int r = 0; r < WIN; ++r) {
-        const uint32_t w[10] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w, c2v.x, c2v.y};
-        if (r + 1 < WIN) load_row(r + 1);                       // prefetch the next row while this one is filtered
+        uint32_t w[12];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(w[4 * c]), "=r"(w[4 * c + 1]), "=r"(w[4 * c + 2]), "=r"(w[4 * c + 3])
+                         : "r"(my_slot + (uint32_t)(r * 3 + c) * slot_stride));
         // ---- realign: drop s leading elements (word shifts by 1 and 2, then a half-word funnel shift)
         uint32_t t1[9], t2[NW + 1], v[NW];
 #pragma unroll
@@ -436,8 +454,15 @@ OFB_API int ofb_corr_lookup(const ofb_pyramid* pyr, const float* coords, float* 
         tile_ok = (P.pitch[l] % 8 == 0) && (P.q_stride[l] % 8 == 0) && ((reinterpret_cast<uintptr_t>(P.base[l]) & 15) == 0);
     if (tile_ok) {
         const int threads = 32 * pyr->levels;
-        if (radius == 4) lookup_tile_kernel<4><<<(int)blocks, threads, 0, st>>>(P, coords, out, idx_or_null, valid_or_null);
-        else lookup_tile_kernel<3><<<(int)blocks, threads, 0, st>>>(P, coords, out, idx_or_null, valid_or_null);
+        const size_t wsm = (size_t)(2 * radius + 3) * 3 * threads * 16;           // window slots: rows x 3 chunks x 16 B
+        static bool configured = false;
+        if (!configured) {
+            OFB_CUDA(cudaFuncSetAttribute(lookup_tile_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 11 * 3 * 128 * 16));
+            OFB_CUDA(cudaFuncSetAttribute(lookup_tile_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 3 * 128 * 16));
+            configured = true;
+        }
+        if (radius == 4) lookup_tile_kernel<4><<<(int)blocks, threads, wsm, st>>>(P, coords, out, idx_or_null, valid_or_null);
+        else lookup_tile_kernel<3><<<(int)blocks, threads, wsm, st>>>(P, coords, out, idx_or_null, valid_or_null);
         OFB_LAUNCH_CHECK();
         return OFB_OK;
     }
