@@ -623,3 +623,72 @@ def test_raft_forward_trace(golden, mode):
             assert np.linalg.norm(out - ref) / np.linalg.norm(ref) <= rtol, it
         up = N(RAFT.upsample_flow(T(g["up_flow"][it]), T(g["up_mask"][it])))
         assert maxabs(up, g["up_out"][it]) <= tol(g["up_out"][it]), it
+
+
+# =============================================================================== memory safety
+def test_kernels_do_not_write_outside_their_buffers():
+    """compute-sanitizer is closed on this GPU pool, so out-of-bounds WRITES are caught with guard bands:
+    every output buffer is carved out of a larger sentinel-filled allocation and the bands must survive.
+    Odd sizes exercise every edge path (partial tiles, partial blocks, padded rows)."""
+    import ctypes
+
+    import ofb200
+    from model.corr import prepare_operands
+
+    lib = ofb200.load()
+    guard = 4096                                                     # elements on each side
+    gen = torch.Generator(device="cuda").manual_seed(31)
+
+    def banded(n, dtype, sentinel):
+        whole = torch.full((n + 2 * guard,), sentinel, dtype=dtype, device="cuda")
+        return whole, whole[guard:guard + n]
+
+    def intact(whole, n, sentinel):
+        ref = torch.full((guard,), sentinel, dtype=whole.dtype, device="cuda")
+        return bool(torch.equal(whole[:guard], ref)) and bool(torch.equal(whole[guard + n:], ref))
+
+    for (b, c, h, w) in [(2, 64, 19, 37), (1, 128, 47, 156), (1, 256, 9, 35)]:
+        f1 = torch.randn((b, c, h, w), device="cuda", generator=gen)
+        f2 = torch.randn((b, c, h, w), device="cuda", generator=gen)
+        a_km, b_km, q_km = prepare_operands(f1, f2, 4)
+        for mode in (1, 2):                                          # padded rows, 8x4 blocks
+            for cg in (1, 2):
+                pyr = ofb200.Pyramid()
+                elems = (ctypes.c_int64 * ofb200.MAX_LEVELS)()
+                ofb200.check(lib.ofb_pyramid_layout(h, w, 4, mode, ctypes.byref(pyr), ctypes.byref(elems)), "layout")
+                pyr.dtype = ofb200.DTYPE_BF16
+                keep = []
+                for lvl in range(4):
+                    n = b * h * w * int(pyr.q_stride[lvl])
+                    whole, view = banded(n, torch.bfloat16, -7.0)
+                    keep.append((whole, n))
+                    pyr.base[lvl] = view.data_ptr()
+                ofb200.check(lib.ofb_corr_pyramid_bf16(ofb200.ptr(a_km), ofb200.ptr(b_km), ofb200.ptr(q_km), ctypes.byref(pyr),
+                                                       b, c, h, w, 1.0, cg, ofb200.stream_ptr()), "pyramid")
+                n_out = b * 324 * h * w
+                whole_o, out = banded(n_out, torch.float32, -7.0)
+                coords = torch.randn((b, 2, h, w), device="cuda", generator=gen) * 30 + 10
+                ofb200.check(lib.ofb_corr_lookup(ctypes.byref(pyr), ofb200.ptr(coords), ofb200.ptr(out), None, None,
+                                                 b, h, w, 4, ofb200.stream_ptr()), "lookup")
+                torch.cuda.synchronize()
+                for whole, n in keep:
+                    assert intact(whole, n, -7.0), (b, c, h, w, mode, cg)
+                assert intact(whole_o, n_out, -7.0) and bool(torch.isfinite(out).all())
+    # streaming kernels at odd sizes
+    for (b, c, h, w) in [(2, 3, 37, 53), (1, 5, 16, 130)]:
+        frame = torch.rand((b, c, h, w), device="cuda", generator=gen)
+        flow = torch.randn((b, 2, h, w), device="cuda", generator=gen) * 0.3
+        for variant in (1, 2, 3):
+            whole, out = banded(b * c * h * w, torch.float32, -7.0)
+            wm, mask = banded(b * h * w, torch.uint8, 200)
+            ofb200.check(lib.ofb_warp_f32(ofb200.ptr(frame), ofb200.ptr(flow), ofb200.ptr(out), ofb200.ptr(mask), b, c, h, w,
+                                          0, 1, 0, 0, variant, 1.0, 1.0, ofb200.stream_ptr()), "warp")
+            torch.cuda.synchronize()
+            assert intact(whole, b * c * h * w, -7.0) and intact(wm, b * h * w, 200), variant
+    n, h, w = 2, 7, 11
+    flow = torch.randn((n, 2, h, w), device="cuda", generator=gen)
+    mask = torch.randn((n, 576, h, w), device="cuda", generator=gen)
+    whole, out = banded(n * 2 * 64 * h * w, torch.float32, -7.0)
+    ofb200.check(lib.ofb_convex_upsample_f32(ofb200.ptr(flow), ofb200.ptr(mask), ofb200.ptr(out), n, h, w, ofb200.stream_ptr()), "up")
+    torch.cuda.synchronize()
+    assert intact(whole, n * 2 * 64 * h * w, -7.0)

@@ -368,7 +368,8 @@ __global__ void __launch_bounds__(128) lookup_tile_kernel(const LookupParams P, 
             const int j = r - k;
             if (j < 0 || j >= D) continue;
             const bool d = (ty.dmask >> j) & 1u;
-            const float vw = k == 0 ? (d ? 0.0f : ty.w0[j]) : k == 1 ? (d ? ty.w0[j] : ty.w1[j]) : (d ? ty.w1[j] : 0.0f);
+            float vw = k == 0 ? (d ? 0.0f : ty.w0[j]) : k == 1 ? (d ? ty.w0[j] : ty.w1[j]) : (d ? ty.w1[j] : 0.0f);
+            if (dead) vw = 0.0f;            // non-finite / far-away coordinates: the weights may be NaN, the result is 0
 #pragma unroll
             for (int i = 0; i < D; ++i) acc[(j % 3)][i] = __fmaf_rn(vw, hrow[i], acc[(j % 3)][i]);
         }

@@ -300,11 +300,20 @@ __global__ void __launch_bounds__(128) warp_rows_kernel(const float* __restrict_
         const float wx1 = s.ix - x0f, wx0 = (x0f + 1.0f) - s.ix;
         const float wy1 = s.iy - y0f, wy0 = (y0f + 1.0f) - s.iy;
         w00[k] = wx0 * wy0; w01[k] = wx1 * wy0; w10[k] = wx0 * wy1; w11[k] = wx1 * wy1;
-        // clamp before the int conversion: zeros padding can leave coordinates far outside; NaN samples nothing
-        const int x0 = (int)fminf(fmaxf(x0f, -2.0f), (float)W + 1.0f), y0 = (int)fminf(fmaxf(y0f, -2.0f), (float)H + 1.0f);
-        const bool fin = x0f == x0f && y0f == y0f;
-        const bool inx0 = fin && x0 >= 0 && x0 < W, inx1 = fin && x0 + 1 >= 0 && x0 + 1 < W;
-        const bool iny0 = y0 >= 0 && y0 < H, iny1 = y0 + 1 >= 0 && y0 + 1 < H;
+        int x0, y0;
+        bool inx0, inx1, iny0, iny1;
+        if (PAD != OFB_PAD_ZEROS) {
+            // border / reflection clip the coordinate into [0, size-1] (NaN clips to 0): the upper-left tap is
+            // always inside, only the +1 taps can fall off the far edge (their weight is 0 there)
+            x0 = (int)x0f; y0 = (int)y0f;
+            inx0 = true; iny0 = true; inx1 = x0 + 1 < W; iny1 = y0 + 1 < H;
+        } else {
+            // clamp before the int conversion: zeros padding can leave coordinates far outside; NaN samples nothing
+            x0 = (int)fminf(fmaxf(x0f, -2.0f), (float)W + 1.0f); y0 = (int)fminf(fmaxf(y0f, -2.0f), (float)H + 1.0f);
+            const bool fin = x0f == x0f && y0f == y0f;
+            inx0 = fin && x0 >= 0 && x0 < W; inx1 = fin && x0 + 1 >= 0 && x0 + 1 < W;
+            iny0 = y0 >= 0 && y0 < H; iny1 = y0 + 1 >= 0 && y0 + 1 < H;
+        }
         inb |= (((iny0 && inx0) ? 1u : 0u) | ((iny0 && inx1) ? 2u : 0u) | ((iny1 && inx0) ? 4u : 0u) |
                 ((iny1 && inx1) ? 8u : 0u)) << (4 * k);
         o00[k] = y0 * W + x0;
