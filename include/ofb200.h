@@ -108,6 +108,11 @@ int ofb_convex_upsample_f32(const float* flow, const float* mask, float* out, in
 int ofb_epe_reduce_f32(const float* pred, const float* target, const float* valid_or_null,
                        double* acc, int B, int H, int W, void* stream);
 int ofb_epe_map_f32(const float* pred, const float* target, float* out, int B, int H, int W, void* stream);
+/* OutlierRatio.update (optical_flow/metrics/f1.py:33-48): acc[0] += number of selected pixels with
+ * epe > abs_threshold and epe / |target| > rel_threshold, acc[1] += number of selected pixels. */
+int ofb_outlier_reduce_f32(const float* pred, const float* target, const float* valid_or_null,
+                           double* acc, int B, int H, int W, float abs_threshold, float rel_threshold,
+                           void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Correlation pyramid layout (owned by the caller, described by ofb_pyramid_layout).

@@ -391,6 +391,28 @@ ORC_API void orc_epe_f32(const float* pred, const float* target, const float* va
     *count_out = cnt;
 }
 
+/* OutlierRatio.update (optical_flow/metrics/f1.py:33-48): outlier = epe > abs_thr and epe / |target| > rel_thr;
+ * masked count of outliers and of selected pixels. */
+ORC_API void orc_outlier_f32(const float* pred, const float* target, const float* valid_or_null, double* sum_out,
+                             int64_t* count_out, int B, int H, int W, float abs_thr, float rel_thr) {
+    const size_t HW = (size_t)H * W;
+    double total = 0.0;
+    int64_t cnt = 0;
+#pragma omp parallel for reduction(+ : total, cnt) schedule(static)
+    for (int64_t q = 0; q < (int64_t)B * (int64_t)HW; ++q) {
+        size_t b = (size_t)q / HW, p = (size_t)q % HW;
+        if (valid_or_null && !(valid_or_null[q] >= 0.5f)) continue;
+        float tx = target[(b * 2 + 0) * HW + p], ty = target[(b * 2 + 1) * HW + p];
+        float dx = pred[(b * 2 + 0) * HW + p] - tx, dy = pred[(b * 2 + 1) * HW + p] - ty;
+        float e = sqrtf(dx * dx + dy * dy);
+        float mag = sqrtf(tx * tx + ty * ty);
+        if (e > abs_thr && (e / mag) > rel_thr) total += 1.0;
+        cnt += 1;
+    }
+    *sum_out = total;
+    *count_out = cnt;
+}
+
 /* Per-pixel EPE map (end_point_error(reduce=False), epe.py:41-61). */
 ORC_API void orc_epe_map_f32(const float* pred, const float* target, float* out, int B, int H, int W) {
     const size_t HW = (size_t)H * W;

@@ -15,6 +15,7 @@ Every function mirrors one reference entry point (paths relative to /root/refere
     upflow8           methods/raft/model/utils.py:89-91
     upsample_flow     methods/raft/model/raft.py:73-85
     end_point_error / epe_sum_count   optical_flow/metrics/epe.py:25-61
+    outlier_sum_count  optical_flow/metrics/f1.py:33-48
 
 All arrays are C-contiguous float32 numpy arrays in the reference's layouts (NCHW).
 """
@@ -61,7 +62,7 @@ _lib = _load()
 for _n in (
     "orc_linspace_f32", "orc_grid_sample_f32", "orc_warp_f32", "orc_resize_bilinear_f32",
     "orc_avg_pool2_f32", "orc_corr_lookup_f32", "orc_convex_upsample_f32", "orc_epe_f32",
-    "orc_epe_map_f32", "orc_round_bf16_f32",
+    "orc_epe_map_f32", "orc_round_bf16_f32", "orc_outlier_f32",
 ):
     getattr(_lib, _n).restype = None
 _lib.orc_linspace_f32.argtypes = [ctypes.c_float, ctypes.c_float, ctypes.c_int, _c_f]
@@ -77,6 +78,8 @@ _lib.orc_convex_upsample_f32.argtypes = [_c_f, _c_f, _c_f] + [ctypes.c_int] * 3
 _lib.orc_epe_f32.argtypes = [_c_f, _c_f, _c_f, ctypes.POINTER(ctypes.c_double),
                              ctypes.POINTER(ctypes.c_int64)] + [ctypes.c_int] * 3
 _lib.orc_epe_map_f32.argtypes = [_c_f, _c_f, _c_f] + [ctypes.c_int] * 3
+_lib.orc_outlier_f32.argtypes = [_c_f, _c_f, _c_f, ctypes.POINTER(ctypes.c_double),
+                                 ctypes.POINTER(ctypes.c_int64)] + [ctypes.c_int] * 3 + [ctypes.c_float] * 2
 _lib.orc_round_bf16_f32.argtypes = [_c_f, _c_f, ctypes.c_int64]
 
 _MODES = {"bilinear": 0, "nearest": 1}
@@ -279,6 +282,19 @@ def epe_sum_count(pred, target, valid=None):
     c = ctypes.c_int64(0)
     _lib.orc_epe_f32(_p(pred), _p(target), _p(v) if v is not None else None,
                      ctypes.byref(s), ctypes.byref(c), b, h, w)
+    return s.value, c.value
+
+
+def outlier_sum_count(pred, target, valid=None, abs_threshold=3.0, rel_threshold=0.05):
+    """optical_flow/metrics/f1.py:33-48 -> (number of outliers, number of selected pixels)."""
+    pred, target = _f32(pred), _f32(target)
+    b, two, h, w = pred.shape
+    assert two == 2 and target.shape == pred.shape
+    v = _f32(valid) if valid is not None else None
+    s = ctypes.c_double(0.0)
+    c = ctypes.c_int64(0)
+    _lib.orc_outlier_f32(_p(pred), _p(target), _p(v) if v is not None else None, ctypes.byref(s), ctypes.byref(c),
+                         b, h, w, abs_threshold, rel_threshold)
     return s.value, c.value
 
 

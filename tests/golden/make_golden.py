@@ -202,6 +202,17 @@ def make_upsample_epe():
     cases["m1_sum"], cases["m1_total"], cases["m1_compute"] = m.sum_epe.clone(), m.total.clone(), m.compute()
     m.update(pred * 0.5, target)
     cases["m2_sum"], cases["m2_total"], cases["m2_compute"] = m.sum_epe.clone(), m.total.clone(), m.compute()
+    # OutlierRatio (f1.py): flows large enough that the 3 px / 5 % thresholds split the pixels
+    from optical_flow.metrics.f1 import OutlierRatio
+    f1_target = 8.0 * torch.randn(3, 2, 11, 17, generator=g(65))
+    f1_pred = f1_target + 3.0 * torch.randn(3, 2, 11, 17, generator=g(66))
+    f1_target[0, :, 0, 0] = 0.0                      # |target| = 0: epe / 0 = inf (an outlier when epe > 3)
+    cases["f1_pred"], cases["f1_target"] = f1_pred, f1_target
+    fm = OutlierRatio(abs_threshold=3.0, rel_threshold=0.05)
+    fm.update(f1_pred, f1_target, valid)
+    cases["f1a_sum"], cases["f1a_total"], cases["f1a_compute"] = fm.sum_outliers.clone(), fm.total.clone(), fm.compute()
+    fm.update(f1_pred, f1_target)
+    cases["f1b_sum"], cases["f1b_total"], cases["f1b_compute"] = fm.sum_outliers.clone(), fm.total.clone(), fm.compute()
     save("upsample_epe", ref_call="RAFT.upsample_flow; optical_flow.metrics.epe.end_point_error / AverageEndPointError", **cases)
 
 

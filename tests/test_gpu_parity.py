@@ -298,6 +298,28 @@ def test_epe_golden(golden):
     assert abs(float(m.compute()) - float(g["m2_compute"])) <= 1e-5
 
 
+def test_outlier_ratio_golden_and_oracle(golden):
+    """OutlierRatio (reference optical_flow/metrics/f1.py): golden vectors from the reference, then a KITTI-size
+    case against the oracle; counts are exact."""
+    from optical_flow.metrics import OutlierRatio
+
+    g = golden("upsample_epe")
+    m = OutlierRatio(abs_threshold=3.0, rel_threshold=0.05)
+    m.update(T(g["f1_pred"]), T(g["f1_target"]), T(g["valid"]))
+    assert float(m.sum_outliers) == float(g["f1a_sum"]) and int(m.total) == int(g["f1a_total"])
+    m.update(T(g["f1_pred"]), T(g["f1_target"]))
+    assert float(m.sum_outliers) == float(g["f1b_sum"]) and int(m.total) == int(g["f1b_total"])
+    assert abs(float(m.compute()) - float(g["f1b_compute"])) <= 1e-6
+    r = rng(17)
+    target = (6 * r.standard_normal((4, 2, 376, 1248))).astype(np.float32)
+    pred = (target + 2.5 * r.standard_normal(target.shape)).astype(np.float32)
+    valid = (r.random((4, 376, 1248)) > 0.2).astype(np.float32)
+    m = OutlierRatio()
+    m.update(T(pred), T(target), T(valid))
+    s, n = oracle.outlier_sum_count(pred, target, valid)
+    assert float(m._acc[0]) == s and int(m.total) == n
+
+
 @pytest.mark.parametrize("shape", [(16, 376, 1248), (3, 11, 17), (2, 1088, 1920)])
 def test_epe_vs_oracle(shape):
     from optical_flow.metrics import AverageEndPointError
