@@ -60,12 +60,11 @@ def algorithmic(pairs):
     n = h8 * w8
     d2 = (2 * RADIUS + 1) ** 2
     return {
-        "corr_pyramid": {
-            "launches": 5,
-            "flops": 2.0 * pairs * n * n * C,
-            # fp32 fmaps read + bf16 operands written and read + bf16 pyramid written
-            "bytes": pairs * (2 * n * C * (4 + 2 + 2) + n * pyramid_elems(h8, w8) * 2),
-        },
+        # K2: bf16 operands read + bf16 pyramid written (both runs: levels 0-1, levels 2-3)
+        "corr_pyramid_kernel": {"launches": 2, "flops": 2.0 * pairs * n * n * C,
+                                "bytes": pairs * (2 * n * C * 2 + n * pyramid_elems(h8, w8) * 2)},
+        # prep: fmap1 and fmap2 read in fp32 (fmap2 twice), K-major bf16 operands written
+        "corr_prep": {"launches": 3, "bytes": pairs * n * C * (3 * 4 + 2 * 2 + 2 / 16)},
         "lookup": {"launches": ITERS,
                    "bytes": ITERS * pairs * n * (LEVELS * (2 * RADIUS + 2) ** 2 * 2 + 8 + LEVELS * d2 * 4)},
         "convex_upsample": {"launches": 1, "bytes": pairs * n * 4 * (576 + 2 + 128)},
@@ -85,7 +84,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -366,19 +365,16 @@ def run_ours(args):
             rec["tflops"] = round(a["flops"] / ms_pass / 1e9, 1)
             rec["tensor_frac_sustained"] = round(rec["tflops"] / PEAKS["bf16_tflops_sustained"], 4)
         kernels.append(rec)
-    k2 = next(r for r in kernels if r["kernel"] == "corr_pyramid")
-    n = h8 * w8
-    k2_bytes = micro * (2 * n * C * 2 + n * pyramid_elems(h8, w8) * 2)   # pyramid kernel alone: bf16 operands + pyramid
-    k2_ms = ksum["corr_pyramid"]["ms_total"] / (ksum["corr_pyramid"]["launches"] / 5)
+    k2 = next(r for r in kernels if r["kernel"] == "corr_pyramid_kernel")
     roofline = {
-        "kernel": "corr_pyramid_kernel (K2 tcgen05: levels 0-1 run + levels 2-3 run; span includes the 3 bf16 prep launches)",
-        "bound": "hbm", "achieved": round(k2_bytes / k2_ms / 1e6, 1), "peak": PEAKS["hbm_gbs"], "unit": "GB/s",
-        "frac": round(k2_bytes / k2_ms / 1e6 / PEAKS["hbm_gbs"], 4), "traffic": None,
+        "kernel": "corr_pyramid_kernel (K2, tcgen05): the levels 0-1 run and the levels 2-3 run of one pyramid build",
+        "bound": "hbm", "achieved": k2["gbs"], "peak": PEAKS["hbm_gbs"], "unit": "GB/s",
+        "frac": k2["hbm_frac"], "traffic": None,
         "peak_source": PEAKS["source"] + " (MEASURED_PEAKS.json hbm_gbs)" if PEAKS["source"] == "measured" else "fallback",
         "tensor": {"achieved": k2["tflops"], "peak": PEAKS["bf16_tflops_sustained"], "unit": "TFLOP/s",
                    "frac": k2["tensor_frac_sustained"]},
         "note": "K=256 makes the builder write-bound: 2*N^2*C flops need 0.39 ms/pair of tensor time, the bf16 "
-                "pyramid write 0.44 ms/pair of HBM time (DESIGN.md section 4)",
+                "pyramid write 0.44 ms/pair of HBM time; measured limit is the SM store path (DESIGN.md section 4)",
     }
     traffic_file = os.path.join(ROOT, "profiles", "k2_traffic.json")
     if os.path.exists(traffic_file):
@@ -422,13 +418,13 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=8, help="image pairs per GPU per step")
     ap.add_argument("--micro", type=int, default=8, help="pairs per pyramid build (device-resident arm)")
     ap.add_argument("--e2e-micro", type=int, default=1, help="pairs per staged micro-batch (host arm)")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cta-group", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-named", action="store_true", help="skip the single-kernel named configs")

@@ -23,6 +23,23 @@ def _default_pyramid_dtype() -> torch.dtype:
     return torch.float32 if os.environ.get("OFB200_PYRAMID_DTYPE", "bf16").lower() in ("fp32", "f32", "float32") else torch.bfloat16
 
 
+# optional ofb200.runner.KernelTimers: when set (bench.py), the prep launches and the pyramid kernel get their own
+# CUDA-event brackets on the launching stream
+TIMERS = None
+
+
+class _NullSpan:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def _span(name: str, launches: int):
+    return TIMERS.span(name, launches) if TIMERS is not None else _NullSpan()
+
+
 def prepare_operands(fmap1: Tensor, fmap2: Tensor, num_levels: int):
     """K-major bf16 operands of the tcgen05 builder: fmap1 * 1/sqrt(C), fmap2, and (for pyramids with
     more than two levels) fmap2 averaged over complete 4x4 blocks.  fp32 (B, C, h, w) CUDA inputs."""
@@ -104,9 +121,11 @@ class CorrBlock:
             self._pyr = pyr
             scale = 1.0 / math.sqrt(float(c))
             if builder == "tcgen05":
-                ops = prepare_operands(fmap1, fmap2, num_levels)
-                rc = lib.ofb_corr_pyramid_bf16(ofb200.ptr(ops[0]), ofb200.ptr(ops[1]), ofb200.ptr(ops[2]),
-                                               ctypes.byref(pyr), b, c, h, w, 1.0, int(cta_group), ofb200.stream_ptr())
+                with _span("corr_prep", 3 if num_levels > 2 else 2):
+                    ops = prepare_operands(fmap1, fmap2, num_levels)
+                with _span("corr_pyramid_kernel", 2 if num_levels > 2 else 1):
+                    rc = lib.ofb_corr_pyramid_bf16(ofb200.ptr(ops[0]), ofb200.ptr(ops[1]), ofb200.ptr(ops[2]),
+                                                   ctypes.byref(pyr), b, c, h, w, 1.0, int(cta_group), ofb200.stream_ptr())
                 ofb200.check(rc, "ofb_corr_pyramid_bf16")
                 # keep the operands alive until the stream has consumed them
                 for t in ops:

@@ -73,9 +73,14 @@ class _NoSpan:
 def hot_path(batch: Dict[str, Tensor], metric: AverageEndPointError, timers: Optional[KernelTimers] = None,
              lookup_out: Optional[Tensor] = None, cta_group: int = 0) -> Dict[str, Tensor]:
     """Run the pass on device tensors.  `batch["coords"]` is (iters, B, 2, h, w)."""
+    import model.corr as corr_mod
+
     sp = (lambda n, k: timers.span(n, k)) if timers is not None else (lambda n, k: _NoSpan())
-    with sp("corr_pyramid", 5):
+    corr_mod.TIMERS = timers                       # CorrBlock brackets its prep launches and the pyramid kernel itself
+    try:
         blk = CorrBlock(batch["fmap1"], batch["fmap2"], num_levels=4, radius=4, cta_group=cta_group)
+    finally:
+        corr_mod.TIMERS = None
     iters = batch["coords"].shape[0]
     corr = None
     with sp("lookup", iters):
