@@ -18,8 +18,9 @@ convex 8x upsampling, backward warp + validity mask of the 3x1088x1920 frame, ma
 `roofline`: the dominant kernel (K2, the tcgen05 correlation-pyramid builder) against the measured
            peaks of MEASURED_PEAKS.json; `kernels` lists every kernel class of the pass the same way
            and the named single-kernel configs (C2 warp, C3 corr, C4 lookup / upsample).
-`cpu_baseline`: the CPU oracle port (oracle/, C + OpenMP + numpy BLAS) on a bounded sample of the
-           same workload, timed on this box's host cores (rank 0, N=1 only).
+`cpu_baseline`: the reference's op sequence on a bounded sample of the same workload, timed on this box's
+           host cores (rank 0, N=1 only) through both CPU restatements under oracle/ -- the C + OpenMP + numpy
+           BLAS oracle and the ATen-op port (the ops the reference itself calls); the faster one is reported.
 """
 import argparse
 import json
@@ -151,6 +152,22 @@ def cpu_pass(sample):
     return oracle.epe_sum_count(flow_up, sample["target"], sample["valid"])
 
 
+def cpu_pass_torch(sample):
+    """The same pass through oracle/torch_port.py: the ATen CPU ops the reference itself calls."""
+    import torch
+
+    from oracle import torch_port as tp
+
+    t = {k: torch.from_numpy(v) for k, v in sample.items()}
+    with torch.no_grad():
+        pyr = tp.corr_pyramid(t["fmap1"], t["fmap2"], LEVELS)
+        for it in range(t["coords"].shape[0]):
+            tp.corr_lookup(pyr, t["coords"][it], RADIUS)
+        flow_up = tp.upsample_flow(t["flow_lo"], t["up_mask"])
+        tp.warp(t["frame"], tp.normalize(flow_up))
+        return tp.epe_sum_count(flow_up, t["target"], t["valid"])
+
+
 def cpu_sample(pairs, seed=99):
     import numpy as np
 
@@ -178,17 +195,26 @@ def host_cores():
 
 
 def time_cpu(steps, warmup, pairs=1):
+    """Both CPU restatements of the reference on one bounded sample; the faster one is the baseline."""
+    import torch
+
+    torch.set_num_threads(host_cores())
     sample = cpu_sample(pairs)
-    for _ in range(warmup):
-        cpu_pass(sample)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        cpu_pass(sample)
-    dt = (time.perf_counter() - t0) / steps
-    return {"value": pairs / dt, "unit": UNIT, "cores": host_cores(), "kind": "port",
+    rates = {}
+    for name, fn in (("c_openmp_numpy", cpu_pass), ("torch_aten", cpu_pass_torch)):
+        for _ in range(warmup):
+            fn(sample)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn(sample)
+        rates[name] = pairs * steps / (time.perf_counter() - t0)
+    best = max(rates, key=rates.get)
+    return {"value": rates[best], "unit": UNIT, "cores": host_cores(), "kind": "port",
             "sample": f"{pairs} pair(s) per step of the same 1080p pass (fp32 volume), {steps} timed step(s) after "
-                      f"{warmup} warm-up, oracle/ C+OpenMP+numpy-BLAS port on all host cores",
-            "s_per_pair": dt / pairs}
+                      f"{warmup} warm-up, all host cores; two restatements of the reference timed, the faster reported: "
+                      + ", ".join(f"{k} {v:.3f} pairs/s" for k, v in rates.items()),
+            "ports": {k: round(v, 4) for k, v in rates.items()},
+            "s_per_pair": 1.0 / rates[best]}
 
 
 def run_reference(args):
@@ -206,7 +232,7 @@ def run_reference(args):
         "steps": steps, "warmup": warm, "ms_per_step": cb["s_per_pair"] * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "pairs_per_step": 1, "iters": ITERS, "radius": RADIUS, "levels": LEVELS},
-        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "ports")},
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -386,7 +412,8 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16 x bf16 -> f32 (corr), f32 (warp/lookup/upsample/EPE)",
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "dtype_detail": "correlation: bf16 x bf16 -> f32 accumulate, bf16 stored; lookup / warp / upsample / EPE: f32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": pairs, "global_pairs_per_step": pairs * world,
                    "micro_batch": micro, "iters": ITERS, "radius": RADIUS, "levels": LEVELS,
@@ -409,7 +436,7 @@ def run_ours(args):
         del batch, views, host, runner
         torch.cuda.empty_cache()
         cb = time_cpu(1, 0, 1)
-        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "ports")}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
