@@ -123,14 +123,21 @@ int ofb_outlier_reduce_f32(const float* pred, const float* target, const float* 
  *                        DRAM atom), blocks raster-ordered:
  *                        base[l] + q*q_stride[l] + ((yy>>2)*(np>>3) + (xx>>3))*32 + (yy&3)*8 + (xx&7)
  *                        -- the lookup's 11x11 window touches ~8 atoms instead of ~15.
+ *   OFB_LAYOUT_QMINOR8X4 the same 8x4 blocks, but block-major / query-minor: with Q = B*h*w queries,
+ *                        base[l] + (((yy>>2)*(np>>3) + (xx>>3))*Q + q)*32 + (yy&3)*8 + (xx&7)
+ *                        (q_stride = 32).  Neighbouring queries' copies of one target block are
+ *                        adjacent: the builder writes 2 KiB runs per warp, a lookup warp (32
+ *                        consecutive queries) reads neighbouring 64-byte slots.
  * ofb_pyramid_layout fills the strides: mode 0 = tight rows (row_pitch = w_l), 1 = padded rows
 * (row_pitch multiple of 16 elements, so every row starts on a 32-byte sector), 2 = padded 8x4
- * blocks (row_pitch multiple of 8, rows padded to a multiple of 4).  elems[l] receives q_stride[l].
+ * blocks (row_pitch multiple of 8, rows padded to a multiple of 4), 3 = the same blocks query-minor.
+ * elems[l] receives the element count of level l PER QUERY (= q_stride[l] except for mode 3).
  * The tensor-core builder needs mode 1 or 2 and writes whole 8-element pieces, i.e. zeros into the
  * padding columns; the bf16 lookup kernel relies on padding columns holding finite values.
  * ------------------------------------------------------------------------------------- */
 #define OFB_LAYOUT_ROWS 0
 #define OFB_LAYOUT_BLOCK8X4 1
+#define OFB_LAYOUT_QMINOR8X4 2
 
 typedef struct ofb_pyramid {
     void* base[OFB_MAX_LEVELS];
@@ -140,7 +147,7 @@ typedef struct ofb_pyramid {
     int32_t lvl_w[OFB_MAX_LEVELS];
     int32_t levels;
     int32_t dtype;  /* OFB_DTYPE_F32 or OFB_DTYPE_BF16 */
-    int32_t layout; /* OFB_LAYOUT_ROWS or OFB_LAYOUT_BLOCK8X4 (bf16 only) */
+    int32_t layout; /* OFB_LAYOUT_ROWS, OFB_LAYOUT_BLOCK8X4 or OFB_LAYOUT_QMINOR8X4 (blocked layouts: bf16 only) */
     int32_t reserved;
 } ofb_pyramid;
 

@@ -50,6 +50,9 @@ def test_pyramid_layout_is_host_only(lib):
     for i in range(4):      # 8x4 blocks: rows padded to a multiple of 4, columns to a multiple of 8
         assert pyr.row_pitch[i] == (pyr.lvl_w[i] + 7) // 8 * 8
         assert pyr.q_stride[i] == pyr.row_pitch[i] * ((pyr.lvl_h[i] + 3) // 4 * 4)
+    assert lib.ofb_pyramid_layout(47, 156, 4, 3, ctypes.byref(pyr), ctypes.byref(elems)) == 0
+    assert pyr.layout == ofb200.LAYOUT_QMINOR8X4 and [pyr.q_stride[i] for i in range(4)] == [32] * 4
+    assert [elems[i] for i in range(4)] == [pyr.row_pitch[i] * ((pyr.lvl_h[i] + 3) // 4 * 4) for i in range(4)]
     assert lib.ofb_pyramid_layout(47, 156, 4, 0, ctypes.byref(pyr), ctypes.byref(elems)) == 0
     assert [pyr.row_pitch[i] for i in range(4)] == [156, 78, 39, 19]
     assert lib.ofb_pyramid_layout(4, 4, 4, 1, ctypes.byref(pyr), ctypes.byref(elems)) != 0   # level 3 would be empty

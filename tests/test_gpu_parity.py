@@ -352,7 +352,7 @@ def _pyramid_from_numpy(levels, dtype, blocked=False):
     pyr = ofb200.Pyramid()
     pyr.levels = len(levels)
     pyr.dtype = ofb200.DTYPE_BF16 if dtype == torch.bfloat16 else ofb200.DTYPE_F32
-    pyr.layout = ofb200.LAYOUT_BLOCK8X4 if blocked else ofb200.LAYOUT_ROWS
+    pyr.layout = (ofb200.LAYOUT_QMINOR8X4 if blocked == "qminor" else ofb200.LAYOUT_BLOCK8X4) if blocked else ofb200.LAYOUT_ROWS
     bufs = []
     for l, lv in enumerate(levels):
         hl, wl = lv.shape[-2:]
@@ -362,10 +362,13 @@ def _pyramid_from_numpy(levels, dtype, blocked=False):
             rows = (hl + 3) & ~3
             img = torch.full((q, rows, pitch), 3.0e38, dtype=dtype, device="cuda")
             img[:, :hl, :wl] = T(lv[:, 0]).to(dtype)
-            buf = img.view(q, rows // 4, 4, pitch // 8, 8).permute(0, 1, 3, 2, 4).contiguous()   # (q, by, bx, y, x)
+            if blocked == "qminor":
+                buf = img.view(q, rows // 4, 4, pitch // 8, 8).permute(1, 3, 0, 2, 4).contiguous()   # (by, bx, q, y, x)
+            else:
+                buf = img.view(q, rows // 4, 4, pitch // 8, 8).permute(0, 1, 3, 2, 4).contiguous()   # (q, by, bx, y, x)
             bufs.append(buf)
             pyr.base[l] = buf.data_ptr()
-            pyr.q_stride[l] = rows * pitch
+            pyr.q_stride[l] = 32 if blocked == "qminor" else rows * pitch
             pyr.row_pitch[l] = pitch
             pyr.lvl_h[l] = hl
             pyr.lvl_w[l] = wl
@@ -424,11 +427,11 @@ def test_lookup_golden_odd_radius3(golden):
     assert np.array_equal(idx, g["odd_idx"]) and np.array_equal(valid, g["odd_valid"])
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, "bf16_blocked"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, "bf16_blocked", "bf16_qminor"])
 @pytest.mark.parametrize("hw", [(47, 156), (55, 128), (24, 40)])
 def test_lookup_vs_oracle(dtype, hw):
     """Seeded pyramid + coords (integer coords, sub-pixel noise, far out of range) vs the oracle."""
-    blocked = dtype == "bf16_blocked"
+    blocked = {"bf16_blocked": True, "bf16_qminor": "qminor"}.get(dtype, False)
     if blocked:
         dtype = torch.bfloat16
     h, w = hw
@@ -673,7 +676,7 @@ def test_kernels_do_not_write_outside_their_buffers():
         f1 = torch.randn((b, c, h, w), device="cuda", generator=gen)
         f2 = torch.randn((b, c, h, w), device="cuda", generator=gen)
         a_km, b_km, q_km = prepare_operands(f1, f2, 4)
-        for mode in (1, 2):                                          # padded rows, 8x4 blocks
+        for mode in (1, 2, 3):                                       # padded rows, 8x4 blocks, query-minor blocks
             for cg in (1, 2):
                 pyr = ofb200.Pyramid()
                 elems = (ctypes.c_int64 * ofb200.MAX_LEVELS)()
@@ -681,7 +684,7 @@ def test_kernels_do_not_write_outside_their_buffers():
                 pyr.dtype = ofb200.DTYPE_BF16
                 keep = []
                 for lvl in range(4):
-                    n = b * h * w * int(pyr.q_stride[lvl])
+                    n = b * h * w * int(elems[lvl])
                     whole, view = banded(n, torch.bfloat16, -7.0)
                     keep.append((whole, n))
                     pyr.base[lvl] = view.data_ptr()

@@ -72,11 +72,12 @@ struct LevelOut {
     __nv_bfloat16* base;
     long long q_stride;
     int pitch, h, w;
-    int blocked;                 // OFB_LAYOUT_BLOCK8X4: a 16-byte piece is one row of an 8x4 block
+    int blocked;                 // 8x4 blocks (OFB_LAYOUT_BLOCK8X4 / QMINOR8X4): a 16-byte piece is one block row
+    long long blk_stride;        // elements between consecutive blocks: 32, or 32 * Q for the query-minor layout
 };
-// element offset of the 8-element piece starting at (y, x), x % 8 == 0
+// element offset (without the query term q * q_stride) of the 8-element piece starting at (y, x), x % 8 == 0
 __device__ __forceinline__ long long piece_offset(const LevelOut& L, int y, int x) {
-    if (L.blocked) return ((long long)(y >> 2) * (L.pitch >> 3) + (x >> 3)) * 32 + (y & 3) * 8;
+    if (L.blocked) return ((long long)(y >> 2) * (L.pitch >> 3) + (x >> 3)) * L.blk_stride + (y & 3) * 8;
     return (long long)y * L.pitch + x;
 }
 
@@ -444,6 +445,10 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int ra_q = lane >> 3;
         const int ra_p = BLK ? ((((lane & 7) & 3) << 1) | ((lane & 7) >> 2)) : (lane & 7);
         const int ra_dy = BLK ? (ra_p >> 1) : (ra_p >> 2), ra_dx = BLK ? (ra_p & 1) * 8 : (ra_p & 3) * 8;
+        // query-minor blocks: one block of 8 consecutive queries per instruction (512 contiguous bytes):
+        // lane = (query lane>>2, block row lane&3)
+        const bool qminor = BLK && P.la.blk_stride != 32;
+        const int qm_q = lane >> 2, qm_s = lane & 3;
         // level B -- 2 lanes per query, 16 queries per instruction
         const int rb_q = lane >> 1, rb_p = lane & 1;
         uint32_t acc = 0, tphase = 0;
@@ -517,25 +522,40 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     const int xb = k / P.YQ, yq = k - xb * P.YQ;
                     const int x0 = (tx * P.XB + xb) * P.CW, y0 = (ty * P.YQ + yq) * P.CR;
                     if (!(PROF && (dbg & 1))) {
-                        const int y = y0 + ra_dy, x = x0 + ra_dx;
                         // pieces are always written whole and the row padding (w..pitch) is written too: TMA
                         // zero-fills targets outside the image, so the padding receives zeros (finite values --
                         // the lookup kernel relies on that) and no 32-byte sector is left partially written
                         // (partial sectors measured a 2x slowdown of the whole kernel at w = 156)
-                        const bool in_img = y < P.la.h && x < P.la.pitch;
-                        const long long off_yx = piece_offset(P.la, y, x);
-                        // all 8 shared loads first, then the 8 global stores: the stores do not wait on each other's data
                         uint4 val[8];
+                        if (qminor) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int r = j * 4 + ra_q;
-                            val[j] = ld_shared_v4(stg_a + (uint32_t)r * 128u + (uint32_t)((ra_p ^ (r & 7)) << 4));
-                        }
+                            for (int j = 0; j < 8; ++j) {
+                                const int r = (j & 3) * 8 + qm_q, p = (qm_s << 1) | (j >> 2);
+                                val[j] = ld_shared_v4(stg_a + (uint32_t)r * 128u + (uint32_t)((p ^ (r & 7)) << 4));
+                            }
+                            const int y = y0 + qm_s;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int r = j * 4 + ra_q;
-                            if (in_img && qrow0 + r < P.Nq)
-                                st_global_v4(P.la.base + (qglob0 + r) * P.la.q_stride + off_yx, val[j]);
+                            for (int j = 0; j < 8; ++j) {
+                                const int r = (j & 3) * 8 + qm_q, x = x0 + (j >> 2) * 8;
+                                if (y < P.la.h && x < P.la.pitch && qrow0 + r < P.Nq)
+                                    st_global_v4(P.la.base + (qglob0 + r) * P.la.q_stride + piece_offset(P.la, y, x), val[j]);
+                            }
+                        } else {
+                            const int y = y0 + ra_dy, x = x0 + ra_dx;
+                            const bool in_img = y < P.la.h && x < P.la.pitch;
+                            const long long off_yx = piece_offset(P.la, y, x);
+                            // all 8 shared loads first, then the 8 global stores: the stores do not wait on each other's data
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int r = j * 4 + ra_q;
+                                val[j] = ld_shared_v4(stg_a + (uint32_t)r * 128u + (uint32_t)((ra_p ^ (r & 7)) << 4));
+                            }
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int r = j * 4 + ra_q;
+                                if (in_img && qrow0 + r < P.Nq)
+                                    st_global_v4(P.la.base + (qglob0 + r) * P.la.q_stride + off_yx, val[j]);
+                            }
                         }
                     }
                     if (P.has_b && !(PROF && (dbg & 2))) {
@@ -633,7 +653,8 @@ int run_gemm(const void* f1_km, const void* f2_km, const ofb_pyramid* pyr, int l
     P.scale = scale; P.apply_scale = (scale != 1.0f) ? 1 : 0;
     // chunk shape follows the output layout (a chunk must be whole 64/128-byte runs of it); tile shape =
     // the arrangement of 4 chunks that covers the image with the fewest tiles (ties: the widest)
-    const bool blk = pyr->layout == OFB_LAYOUT_BLOCK8X4;
+    const bool blk = pyr->layout != OFB_LAYOUT_ROWS;
+    const long long blk_stride = pyr->layout == OFB_LAYOUT_QMINOR8X4 ? 32LL * B * Nq : 32LL;
     P.CW = blk ? 16 : 32; P.CR = blk ? 4 : 2;
     long long best = -1;
     for (int xb = 1; xb <= 4; xb *= 2) {
@@ -672,12 +693,12 @@ int run_gemm(const void* f1_km, const void* f2_km, const ofb_pyramid* pyr, int l
     P.n_items = (int)n_items;
     P.la.base = reinterpret_cast<__nv_bfloat16*>(pyr->base[la_idx]);
     P.la.q_stride = pyr->q_stride[la_idx]; P.la.pitch = pyr->row_pitch[la_idx];
-    P.la.h = pyr->lvl_h[la_idx]; P.la.w = pyr->lvl_w[la_idx]; P.la.blocked = pyr->layout == OFB_LAYOUT_BLOCK8X4;
+    P.la.h = pyr->lvl_h[la_idx]; P.la.w = pyr->lvl_w[la_idx]; P.la.blocked = blk; P.la.blk_stride = blk_stride;
     P.has_b = lb_idx >= 0 ? 1 : 0;
     if (P.has_b) {
         P.lb.base = reinterpret_cast<__nv_bfloat16*>(pyr->base[lb_idx]);
         P.lb.q_stride = pyr->q_stride[lb_idx]; P.lb.pitch = pyr->row_pitch[lb_idx];
-        P.lb.h = pyr->lvl_h[lb_idx]; P.lb.w = pyr->lvl_w[lb_idx]; P.lb.blocked = P.la.blocked;
+        P.lb.h = pyr->lvl_h[lb_idx]; P.lb.w = pyr->lvl_w[lb_idx]; P.lb.blocked = blk; P.lb.blk_stride = blk_stride;
     }
     P.prof = prof ? prof + (size_t)prof_slot * PROF_SLOT : nullptr;
     P.dbg = 0;
@@ -727,10 +748,11 @@ int corr_pyramid_impl(const void* f1_km, const void* f2_km, const void* f2q_km, 
         // 16-byte store pieces: rows and query slices start on 8-element boundaries
         if ((pyr->row_pitch[l] & 7) || (pyr->q_stride[l] & 7) || (reinterpret_cast<uintptr_t>(pyr->base[l]) & 15))
             return OFB_EALIGN;
-        const int rows = pyr->layout == OFB_LAYOUT_BLOCK8X4 ? ((pyr->lvl_h[l] + 3) & ~3) : pyr->lvl_h[l];
-        if (pyr->q_stride[l] < (int64_t)pyr->row_pitch[l] * rows) return OFB_EINVAL;
+        const int rows = pyr->layout != OFB_LAYOUT_ROWS ? ((pyr->lvl_h[l] + 3) & ~3) : pyr->lvl_h[l];
+        if (pyr->layout == OFB_LAYOUT_QMINOR8X4 ? pyr->q_stride[l] != 32 : pyr->q_stride[l] < (int64_t)pyr->row_pitch[l] * rows)
+            return OFB_EINVAL;
     }
-    if (pyr->layout != OFB_LAYOUT_ROWS && pyr->layout != OFB_LAYOUT_BLOCK8X4) return OFB_EINVAL;
+    if (pyr->layout < OFB_LAYOUT_ROWS || pyr->layout > OFB_LAYOUT_QMINOR8X4) return OFB_EINVAL;
     // auto: one CTA per tile -- measured faster than the CTA pair on every BASELINE shape once the
     // kernel became HBM-write-bound (profiles/r01_k2_findings.md); the pair halves operand traffic but
     // couples two epilogues through one accumulator barrier

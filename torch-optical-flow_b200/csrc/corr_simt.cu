@@ -180,9 +180,9 @@ OFB_API int ofb_corr_prep_bf16(const float* fmap_nchw, void* out_km_bf16, int B,
 }
 
 OFB_API int ofb_pyramid_layout(int h, int w, int levels, int mode, ofb_pyramid* pyr, int64_t elems[OFB_MAX_LEVELS]) {
-    if (!pyr || h <= 0 || w <= 0 || levels < 1 || levels > OFB_MAX_LEVELS || mode < 0 || mode > 2) return OFB_EINVAL;
+    if (!pyr || h <= 0 || w <= 0 || levels < 1 || levels > OFB_MAX_LEVELS || mode < 0 || mode > 3) return OFB_EINVAL;
     pyr->levels = levels;
-    pyr->layout = mode == 2 ? OFB_LAYOUT_BLOCK8X4 : OFB_LAYOUT_ROWS;
+    pyr->layout = mode == 2 ? OFB_LAYOUT_BLOCK8X4 : mode == 3 ? OFB_LAYOUT_QMINOR8X4 : OFB_LAYOUT_ROWS;
     pyr->reserved = 0;
     for (int l = 0; l < OFB_MAX_LEVELS; ++l) {
         pyr->base[l] = nullptr;
@@ -193,11 +193,11 @@ OFB_API int ofb_pyramid_layout(int h, int w, int levels, int mode, ofb_pyramid* 
         const int hl = h >> l, wl = w >> l;
         if (hl <= 0 || wl <= 0) return OFB_EINVAL;   // F.avg_pool2d raises "Output size is too small" (corr.py:53)
         // padded rows start on 32-byte sectors (bf16); 8x4 blocks are 64-byte aligned by construction
-        const int pitch = mode == 1 ? ((wl + 15) & ~15) : mode == 2 ? ((wl + 7) & ~7) : wl;
-        const int rows = mode == 2 ? ((hl + 3) & ~3) : hl;
+        const int pitch = mode == 1 ? ((wl + 15) & ~15) : mode >= 2 ? ((wl + 7) & ~7) : wl;
+        const int rows = mode >= 2 ? ((hl + 3) & ~3) : hl;
         pyr->lvl_h[l] = hl; pyr->lvl_w[l] = wl; pyr->row_pitch[l] = pitch;
-        pyr->q_stride[l] = (int64_t)pitch * rows;
-        if (elems) elems[l] = pyr->q_stride[l];      // per query; caller multiplies by B*h*w
+        pyr->q_stride[l] = mode == 3 ? 32 : (int64_t)pitch * rows;
+        if (elems) elems[l] = (int64_t)pitch * rows;  // per query; caller multiplies by B*h*w
     }
     return OFB_OK;
 }

@@ -43,7 +43,8 @@ struct LookupParams {
     int lh[OFB_MAX_LEVELS];
     int lw[OFB_MAX_LEVELS];
     int levels, radius, B, h, w;
-    int blocked;   // OFB_LAYOUT_BLOCK8X4 (register-tile kernel only)
+    int blocked;   // 8x4-blocked layouts (register-tile kernel only)
+    long long blk_stride;   // elements between consecutive blocks: 32, or 32 * Q (query-minor)
 };
 
 template <typename T> struct Elem;
@@ -317,14 +318,14 @@ __global__ void __launch_bounds__(128) lookup_tile_kernel(const LookupParams P, 
     const uint32_t my_slot = (uint32_t)__cvta_generic_to_shared(win_smem) + threadIdx.x * 16u;
     const uint32_t slot_stride = blockDim.x * 16u;
     {
-        const int cstep = P.blocked ? 32 : 8;
+        const long long cstep = P.blocked ? P.blk_stride : 8;
 #pragma unroll
         for (int r = 0; r < WIN; ++r) {
             const int y = ys + r;
             const bool rok = !dead && r < wrows && y >= 0 && y < Hl;
             // an aligned 8-element chunk is one row of an 8x4 block (blocked) or 8 consecutive row elements
             const __nv_bfloat16* row = P.blocked
-                ? slice + ((long long)(y >> 2) * (pitch >> 3) + (xa >> 3)) * 32 + (y & 3) * 8
+                ? slice + ((long long)(y >> 2) * (pitch >> 3) + (xa >> 3)) * P.blk_stride + (y & 3) * 8
                 : slice + (long long)y * pitch + xa;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
@@ -426,8 +427,9 @@ OFB_API int ofb_corr_lookup(const ofb_pyramid* pyr, const float* coords, float* 
     if (B == 0) return OFB_OK;
     LookupParams P;
     P.levels = pyr->levels; P.radius = radius; P.B = B; P.h = h; P.w = w;
-    P.blocked = pyr->layout == OFB_LAYOUT_BLOCK8X4;
-    if (pyr->layout != OFB_LAYOUT_ROWS && pyr->layout != OFB_LAYOUT_BLOCK8X4) return OFB_EINVAL;
+    P.blocked = pyr->layout != OFB_LAYOUT_ROWS;
+    P.blk_stride = pyr->layout == OFB_LAYOUT_QMINOR8X4 ? 32LL * B * h * w : 32LL;
+    if (pyr->layout < OFB_LAYOUT_ROWS || pyr->layout > OFB_LAYOUT_QMINOR8X4) return OFB_EINVAL;
     for (int l = 0; l < OFB_MAX_LEVELS; ++l) {
         const bool on = l < pyr->levels;
         P.base[l] = on ? pyr->base[l] : nullptr;

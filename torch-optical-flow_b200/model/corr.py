@@ -102,9 +102,10 @@ class CorrBlock:
 
         pyr = ofb200.Pyramid()
         elems = (ctypes.c_int64 * ofb200.MAX_LEVELS)()
-        # tcgen05 builder: 8x4-blocked bf16 levels (what the lookup kernel reads with the fewest DRAM atoms);
-        # CUDA-core builder: padded rows
-        mode = 2 if (builder == "tcgen05" and radius in (3, 4)) else 1
+        # tcgen05 builder: 8x4-blocked bf16 levels (what the lookup kernel reads with the fewest DRAM atoms),
+        # query-minor by default (OFB200_PYRAMID_LAYOUT=blocked|qminor); CUDA-core builder: padded rows
+        blocked_mode = 2 if os.environ.get("OFB200_PYRAMID_LAYOUT", "qminor").lower() == "blocked" else 3
+        mode = blocked_mode if (builder == "tcgen05" and radius in (3, 4)) else 1
         ofb200.check(lib.ofb_pyramid_layout(h, w, num_levels, mode, ctypes.byref(pyr), ctypes.byref(elems)), "ofb_pyramid_layout")
         pyr.dtype = ofb200.DTYPE_BF16 if pyramid_dtype == torch.bfloat16 else ofb200.DTYPE_F32
         n = h * w
@@ -115,7 +116,7 @@ class CorrBlock:
                 # the tcgen05 builder writes the row padding itself (zeros); the CUDA-core builder does not,
                 # and the lookup kernel requires finite values there
                 alloc = torch.empty if builder == "tcgen05" else torch.zeros
-                buf = alloc(b * n * int(pyr.q_stride[lvl]), dtype=pyramid_dtype, device=self._dev)
+                buf = alloc(b * n * int(elems[lvl]), dtype=pyramid_dtype, device=self._dev)
                 self._buffers.append(buf)
                 pyr.base[lvl] = buf.data_ptr()
             self._pyr = pyr
@@ -152,7 +153,12 @@ class CorrBlock:
             for lvl, buf in enumerate(self._buffers):
                 qs, pitch = int(self._pyr.q_stride[lvl]), int(self._pyr.row_pitch[lvl])
                 hl, wl = int(self._pyr.lvl_h[lvl]), int(self._pyr.lvl_w[lvl])
-                if self._pyr.layout == ofb200.LAYOUT_BLOCK8X4:
+                if self._pyr.layout == ofb200.LAYOUT_QMINOR8X4:
+                    rows = buf.numel() // (b * n * pitch)
+                    blocks = buf.view(rows // 4, pitch // 8, b * n, 4, 8)                  # (by, bx, q, y, x)
+                    img = blocks.permute(2, 0, 3, 1, 4).reshape(b * n, rows, pitch)
+                    views.append(img[:, :hl, :wl].unsqueeze(1))
+                elif self._pyr.layout == ofb200.LAYOUT_BLOCK8X4:
                     blocks = buf.view(b * n, qs // (4 * pitch), pitch // 8, 4, 8)          # (q, by, bx, y, x)
                     img = blocks.permute(0, 1, 3, 2, 4).reshape(b * n, qs // pitch, pitch)
                     views.append(img[:, :hl, :wl].unsqueeze(1))

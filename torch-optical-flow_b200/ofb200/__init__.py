@@ -18,7 +18,7 @@ CSRC = os.path.join(os.path.dirname(_HERE), "csrc")
 MODE = {"bilinear": 0, "nearest": 1}
 PAD = {"zeros": 0, "border": 1, "reflection": 2}
 DTYPE_F32, DTYPE_BF16 = 0, 1
-LAYOUT_ROWS, LAYOUT_BLOCK8X4 = 0, 1
+LAYOUT_ROWS, LAYOUT_BLOCK8X4, LAYOUT_QMINOR8X4 = 0, 1, 2
 MAX_LEVELS = 4
 
 _vp = ctypes.c_void_p
