@@ -11,7 +11,7 @@
 //   * operands are K-major bf16 (ofb_corr_prep_bf16: cast + transpose, 1/sqrt(C) folded into fmap1),
 //     fetched by TMA with 128-byte swizzle;
 //   * a CTA owns 128 queries (rows of the volume): their 128 x C slice of fmap1 stays RESIDENT in
-//     shared memory while the CTA walks target tiles; only fmap2 streams through a 3..7 stage ring;
+//     shared memory while the CTA walks target tiles; only fmap2 streams through a 96..160 KiB TMA ring;
 //   * a target tile is 256 targets laid out as 4 "chunks" of 2 rows x 32 columns of the target image
 //     (tile shape 32x8, 64x4 or 128x2, whichever wastes least for the image width), fetched as 4-D TMA
 //     boxes (C, x, y, b).  TMA zero-fills outside the image;
@@ -21,10 +21,14 @@
 //     across the pair) -- halves the L2 -> SM operand traffic, which is what bounds cta_group = 1
 //     (measured: 37 B/cycle/SM, profiles/r01_k2_findings.md);
 //   * epilogue: 8 warps; a thread owns one query row and one 64-column chunk at a time
-//     (tcgen05.ld 32x32b.x64).  A chunk is 2 image rows x 32 columns, so the 2x2 means are sums of
-//     registers of ONE thread.  Output leaves through the LSU, not TMA (TMA tensor stores cost ~5
-//     cycles per box row and these rows are 64 bytes): each warp transposes its 32 x 128 B through a
-//     private XOR-swizzled shared-memory stage and writes 16-byte pieces, 4 lanes per 64-byte segment.
+//     (tcgen05.ld 32x32b.x64).  A chunk is a pool-closed patch of the target image (16 x 4 for the 8x4-blocked
+//     layouts, 32 x 2 for rows), so the 2x2 means are sums of registers of ONE thread.  Output leaves through
+//     the LSU, not TMA (TMA tensor stores cost ~5 cycles per box row and these rows are 64 bytes):
+//       - query-minor blocked layout (default): the lane's two 64-byte block slots are its own and the 32 lanes'
+//         slots are adjacent, so every lane stores full 32-byte sectors straight from registers
+//         (st.global.v8.b32) -- no shared-memory transpose, no barriers; a warp fills 2 KiB runs;
+//       - query-major layouts: each warp transposes its 32 x 128 B through a private XOR-swizzled
+//         shared-memory stage and writes 16-byte pieces, 8 lanes per 128-byte run.
 //
 // Roofline: 2*B*N^2*C flops against the bf16 tensor peak and 2 bytes * 1.33 *
 // B*N^2 of pyramid writes against HBM; at C = 256 and 1965 MHz the write is the larger bound.
@@ -48,7 +52,7 @@ constexpr int B_TILE_KB_BYTES = TILE_N * BLOCK_K * 2;      // 32 KiB per k-block
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;       // warp 0: TMA, warp 1: MMA + TMEM, warps 2..9: epilogue
 constexpr int TMEM_COLS = 512;
-constexpr int MAX_STAGES = 8;
+constexpr int MAX_STAGES = 10;
 constexpr int PROF_SLOT = 148 * 16;         // uint64 counters per GEMM run in the diagnostics buffer
 
 constexpr int STG_A_BYTES = 32 * 128;       // per warp: 32 queries x (2 rows x 32 bf16)
@@ -57,16 +61,20 @@ constexpr int STG_WARP_BYTES = STG_A_BYTES + STG_B_BYTES;
 
 constexpr int OFF_A = 0;
 constexpr int OFF_B = OFF_A + MAX_KB * A_KB_BYTES;         // 64 KiB, 1024-aligned
-template <int CG> struct Ring {
+// The query-minor layout needs no epilogue staging (direct register stores): its shared memory goes to a deeper
+// operand ring instead (the stream is latency-bound: 2 / 3 stages of 32 KiB measured 6900 / 5000 cycles per tile).
+template <int CG, int LAY> struct Ring {
+    static constexpr bool STAGED = LAY != OFB_LAYOUT_QMINOR8X4;
     static constexpr int STAGE_BYTES = B_TILE_KB_BYTES / CG;              // 32 KiB / 16 KiB
-    static constexpr int STAGES = CG == 1 ? 3 : 7;                         // 96 KiB / 112 KiB
+    static constexpr int STAGES = (STAGED ? 3 : 5) * CG;                  // 96 KiB, or 160 KiB without the staging area
     static constexpr int OFF_STG = OFF_B + STAGES * STAGE_BYTES;
-    static constexpr int OFF_BAR = OFF_STG + NUM_EPI_WARPS * STG_WARP_BYTES;
+    static constexpr int OFF_BAR = OFF_STG + (STAGED ? NUM_EPI_WARPS * STG_WARP_BYTES : 0);
     static constexpr int NUM_BARS = 2 + 2 * MAX_STAGES + 4;                // a_full, a_empty, b_full[], b_empty[], t_full[2], t_empty[2]
     static constexpr int SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16;
     static constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;                   // manual 1024-byte alignment of the dynamic segment
 };
-static_assert(Ring<1>::SMEM_ALLOC <= 232448 && Ring<2>::SMEM_ALLOC <= 232448, "shared memory budget");
+static_assert(Ring<1, 0>::SMEM_ALLOC <= 232448 && Ring<2, 0>::SMEM_ALLOC <= 232448 && Ring<1, 2>::SMEM_ALLOC <= 232448 &&
+              Ring<2, 2>::SMEM_ALLOC <= 232448 && Ring<2, 2>::STAGES <= MAX_STAGES, "shared memory budget");
 
 struct LevelOut {
     __nv_bfloat16* base;
@@ -287,6 +295,12 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
 __device__ __forceinline__ void st_global_v4(void* p, uint4 v) {
     asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// 32-byte store (sm_100): one full sector per lane
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t* a, const uint32_t* b) {
+    asm volatile("st.global.cs.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]) : "memory");
+}
+
 struct ItemCoord {
     int b, chunk, m;
 };
@@ -300,11 +314,13 @@ __device__ __forceinline__ ItemCoord decode_item(const GemmParams& P, int item) 
 }
 
 // ------------------------------------------------------------------------------------ the kernel
-template <int CG, bool PROF, bool BLK>
+// LAY: output layout (OFB_LAYOUT_ROWS / BLOCK8X4 / QMINOR8X4)
+template <int CG, bool PROF, int LAY>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const GemmParams P) {
-    using R = Ring<CG>;
+    using R = Ring<CG, LAY>;
+    constexpr bool BLK = LAY != OFB_LAYOUT_ROWS;
     extern __shared__ uint8_t smem_raw[];
     // the 128-byte swizzle is a function of the absolute shared address: align the segment to 1024
     const uint32_t raw = smem_u32(smem_raw);
@@ -447,7 +463,7 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int ra_dy = BLK ? (ra_p >> 1) : (ra_p >> 2), ra_dx = BLK ? (ra_p & 1) * 8 : (ra_p & 3) * 8;
         // query-minor blocks: one block of 8 consecutive queries per instruction (512 contiguous bytes):
         // lane = (query lane>>2, block row lane&3)
-        const bool qminor = BLK && P.la.blk_stride != 32;
+        constexpr bool qminor = LAY == OFB_LAYOUT_QMINOR8X4;
         const int qm_q = lane >> 2, qm_s = lane & 3;
         // level B -- 2 lanes per query, 16 queries per instruction
         const int rb_q = lane >> 1, rb_p = lane & 1;
@@ -491,6 +507,43 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     } else {
 #pragma unroll
                         for (int c = 0; c < 64; ++c) f[c] = __uint_as_float(v[c]);
+                    }
+                    if (qminor && !(PROF && (dbg & 64))) {
+                        // ---- query-minor blocks: a lane's two 64-byte block slots are its own, and the 32 lanes'
+                        // slots are adjacent -- store straight from registers, one full 32-byte sector (two block rows)
+                        // per lane and instruction; no shared-memory transpose, no barriers
+                        const int xb = k / P.YQ, yq = k - xb * P.YQ;
+                        const int x0 = (tx * P.XB + xb) * P.CW, y0 = (ty * P.YQ + yq) * P.CR;
+                        uint32_t pk[32];
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) pk[c] = pack_bf16(f[2 * c], f[2 * c + 1]);
+                        const bool qok = qrow0 + lane < P.Nq;
+                        if (!(PROF && (dbg & 1))) {
+#pragma unroll
+                            for (int b2 = 0; b2 < 2; ++b2) {
+                                const int x = x0 + b2 * 8;
+                                if (qok && y0 < P.la.h && x < P.la.pitch) {
+                                    __nv_bfloat16* dst = P.la.base + (qglob0 + lane) * P.la.q_stride + piece_offset(P.la, y0, x);
+                                    // register piece (block row yy, block b2) = pk[4 * (2 * yy + b2) ..]
+                                    st_global_v8(dst, pk + 4 * b2, pk + 4 * (2 + b2));
+                                    st_global_v8(dst + 16, pk + 4 * (4 + b2), pk + 4 * (6 + b2));
+                                }
+                            }
+                        }
+                        if (P.has_b && !(PROF && (dbg & 2))) {
+                            uint32_t mk[8];
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {       // pooled 2 rows x 8 columns: 2x2 means in raster order / 4
+                                const int a0 = ((2 * c) >> 3) * 32 + ((2 * c) & 7) * 2, a1 = ((2 * c + 1) >> 3) * 32 + ((2 * c + 1) & 7) * 2;
+                                const float m0 = (((f[a0] + f[a0 + 1]) + f[a0 + 16]) + f[a0 + 17]) * 0.25f;
+                                const float m1 = (((f[a1] + f[a1 + 1]) + f[a1 + 16]) + f[a1 + 17]) * 0.25f;
+                                mk[c] = pack_bf16(m0, m1);
+                            }
+                            const int y = y0 >> 1, x = x0 >> 1;
+                            if (qok && y < P.lb.h && x < P.lb.pitch)
+                                st_global_v8(P.lb.base + (qglob0 + lane) * P.lb.q_stride + piece_offset(P.lb, y, x), mk, mk + 4);
+                        }
+                        continue;
                     }
                     // ---- registers -> swizzled stage.  chunk = 2 image rows x 32 columns, piece p = 8 bf16
                     if (!(PROF && (dbg & 16))) {
@@ -619,18 +672,18 @@ bool encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims
     return r == CUDA_SUCCESS;
 }
 
-template <int CG, bool PROF, bool BLK>
+template <int CG, bool PROF, int LAY>
 int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& P, int grid, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        OFB_CUDA(cudaFuncSetAttribute(corr_pyramid_kernel<CG, PROF, BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      Ring<CG>::SMEM_ALLOC));
+        OFB_CUDA(cudaFuncSetAttribute(corr_pyramid_kernel<CG, PROF, LAY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      Ring<CG, LAY>::SMEM_ALLOC));
         configured = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = Ring<CG>::SMEM_ALLOC;
+    cfg.dynamicSmemBytes = Ring<CG, LAY>::SMEM_ALLOC;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -639,7 +692,7 @@ int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    OFB_CUDA(cudaLaunchKernelEx(&cfg, corr_pyramid_kernel<CG, PROF, BLK>, ma, mb, P));
+    OFB_CUDA(cudaLaunchKernelEx(&cfg, corr_pyramid_kernel<CG, PROF, LAY>, ma, mb, P));
     OFB_LAUNCH_CHECK();
     return OFB_OK;
 }
@@ -722,10 +775,12 @@ int run_gemm(const void* f1_km, const void* f2_km, const ofb_pyramid* pyr, int l
     }
     int grid = workers * cg;
     if ((long long)grid > n_items * cg) grid = (int)(n_items * cg);
-#define OFB_GEMM_CASE(CGV, PROFV, BLKV) \
-    if (cg == CGV && (prof != nullptr) == PROFV && blk == BLKV) return launch_gemm<CGV, PROFV, BLKV>(ma, mb, P, grid, st);
-    OFB_GEMM_CASE(1, false, false) OFB_GEMM_CASE(1, false, true) OFB_GEMM_CASE(2, false, false) OFB_GEMM_CASE(2, false, true)
-    OFB_GEMM_CASE(1, true, false) OFB_GEMM_CASE(1, true, true) OFB_GEMM_CASE(2, true, false) OFB_GEMM_CASE(2, true, true)
+#define OFB_GEMM_CASE(CGV, PROFV, LAYV) \
+    if (cg == CGV && (prof != nullptr) == PROFV && pyr->layout == LAYV) return launch_gemm<CGV, PROFV, LAYV>(ma, mb, P, grid, st);
+    OFB_GEMM_CASE(1, false, 0) OFB_GEMM_CASE(1, false, 1) OFB_GEMM_CASE(1, false, 2)
+    OFB_GEMM_CASE(2, false, 0) OFB_GEMM_CASE(2, false, 1) OFB_GEMM_CASE(2, false, 2)
+    OFB_GEMM_CASE(1, true, 0) OFB_GEMM_CASE(1, true, 1) OFB_GEMM_CASE(1, true, 2)
+    OFB_GEMM_CASE(2, true, 0) OFB_GEMM_CASE(2, true, 1) OFB_GEMM_CASE(2, true, 2)
 #undef OFB_GEMM_CASE
     return OFB_EINVAL;
 }
