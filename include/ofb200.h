@@ -127,7 +127,8 @@ int ofb_outlier_reduce_f32(const float* pred, const float* target, const float* 
  *                        base[l] + (((yy>>2)*(np>>3) + (xx>>3))*Q + q)*32 + (yy&3)*8 + (xx&7)
  *                        (q_stride = 32).  Neighbouring queries' copies of one target block are
  *                        adjacent: the builder writes 2 KiB runs per warp, a lookup warp (32
- *                        consecutive queries) reads neighbouring 64-byte slots.
+ *                        consecutive queries) reads neighbouring 64-byte slots.  Level bases must be
+ *                        32-byte aligned.
  * ofb_pyramid_layout fills the strides: mode 0 = tight rows (row_pitch = w_l), 1 = padded rows
 * (row_pitch multiple of 16 elements, so every row starts on a 32-byte sector), 2 = padded 8x4
  * blocks (row_pitch multiple of 8, rows padded to a multiple of 4), 3 = the same blocks query-minor.

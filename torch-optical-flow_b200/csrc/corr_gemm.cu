@@ -801,7 +801,8 @@ int corr_pyramid_impl(const void* f1_km, const void* f2_km, const void* f2q_km, 
         if (!pyr->base[l] || pyr->lvl_h[l] != (h >> l) || pyr->lvl_w[l] != (w >> l)) return OFB_EINVAL;
         if (pyr->lvl_h[l] <= 0 || pyr->lvl_w[l] <= 0 || pyr->row_pitch[l] < pyr->lvl_w[l]) return OFB_EINVAL;
         // 16-byte store pieces: rows and query slices start on 8-element boundaries
-        if ((pyr->row_pitch[l] & 7) || (pyr->q_stride[l] & 7) || (reinterpret_cast<uintptr_t>(pyr->base[l]) & 15))
+        const uintptr_t amask = pyr->layout == OFB_LAYOUT_QMINOR8X4 ? 31 : 15;   // query-minor: 32-byte sector stores
+        if ((pyr->row_pitch[l] & 7) || (pyr->q_stride[l] & 7) || (reinterpret_cast<uintptr_t>(pyr->base[l]) & amask))
             return OFB_EALIGN;
         const int rows = pyr->layout != OFB_LAYOUT_ROWS ? ((pyr->lvl_h[l] + 3) & ~3) : pyr->lvl_h[l];
         if (pyr->layout == OFB_LAYOUT_QMINOR8X4 ? pyr->q_stride[l] != 32 : pyr->q_stride[l] < (int64_t)pyr->row_pitch[l] * rows)
