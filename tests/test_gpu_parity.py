@@ -717,3 +717,87 @@ def test_kernels_do_not_write_outside_their_buffers():
     ofb200.check(lib.ofb_convex_upsample_f32(ofb200.ptr(flow), ofb200.ptr(mask), ofb200.ptr(out), n, h, w, ofb200.stream_ptr()), "up")
     torch.cuda.synchronize()
     assert intact(whole, n * 2 * 64 * h * w, -7.0)
+
+
+# =============================================================================== randomized sweep
+@pytest.mark.parametrize("seed", list(range(12)))
+def test_random_shapes_corr_block_and_lookup(seed, monkeypatch):
+    """Random (B, C, h, w), level count, radius, layout and CTA shape: the tcgen05 pyramid against the fp32
+    CUDA-core builder, and the lookup on the stored pyramid against the oracle (indices and masks bit-exact)."""
+    from model.corr import CorrBlock
+
+    r = rng(1000 + seed)
+    c = int(r.choice([64, 128, 192, 256]))
+    h, w = int(r.integers(8, 70)), int(r.integers(8, 170))
+    b = int(r.integers(1, 4))
+    levels = int(r.integers(1, 5))
+    while (h >> (levels - 1)) < 2 or (w >> (levels - 1)) < 2:     # keep every level at least 2x2 (1x1 divides by zero)
+        levels -= 1
+    radius = int(r.choice([3, 4]))
+    monkeypatch.setenv("OFB200_PYRAMID_LAYOUT", str(r.choice(["qminor", "blocked"])))
+    cta_group = int(r.choice([1, 2]))
+    gen = torch.Generator(device="cuda").manual_seed(seed)
+    f1 = torch.randn((b, c, h, w), device="cuda", generator=gen)
+    f2 = torch.randn((b, c, h, w), device="cuda", generator=gen)
+    ref_blk = CorrBlock(f1, f2, num_levels=levels, radius=radius, pyramid_dtype=torch.float32, builder="simt")
+    blk = CorrBlock(f1, f2, num_levels=levels, radius=radius, cta_group=cta_group)
+    assert blk.builder == "tcgen05"
+    torch.cuda.synchronize()
+    info = (b, c, h, w, levels, radius, cta_group)
+    for lvl, (rel, mx) in enumerate(_pyr_errors(blk.corr_pyramid, [N(p) for p in ref_blk.corr_pyramid])):
+        assert rel <= 4e-3 and mx <= 4e-2, (info, lvl, rel, mx)
+    coords = (oracle.coords_grid(b, h, w) + float(r.choice([0.0, 0.5, 3.0, 25.0])) * r.standard_normal((b, 2, h, w))).astype(np.float32)
+    out, idx, valid = blk(T(coords), return_index=True)
+    stored = [np.ascontiguousarray(N(p.float())) for p in blk.corr_pyramid]
+    ref, ridx, rvalid = oracle.corr_lookup(stored, coords, radius=radius, return_index=True)
+    assert np.array_equal(N(idx), ridx) and np.array_equal(N(valid), rvalid), info
+    assert maxabs(N(out), ref) <= tol(ref), info
+
+
+@pytest.mark.parametrize("seed", list(range(8)))
+def test_random_shapes_streaming_kernels(seed):
+    """Random shapes / options for warp (every kernel variant), resize, convex upsampling and the metric reductions
+    against the oracle."""
+    from model.raft import upsample_flow
+    from optical_flow import normalize, resize, warp
+    from optical_flow.metrics import AverageEndPointError, OutlierRatio
+
+    r = rng(2000 + seed)
+    b, c = int(r.integers(1, 4)), int(r.integers(1, 6))
+    h, w = int(r.integers(2, 90)), int(r.integers(2, 200))
+    pad = str(r.choice(["zeros", "border", "reflection"]))
+    ac = bool(r.integers(0, 2))
+    frame = r.random((b, c, h, w), dtype=np.float32)
+    flow_px = (float(r.choice([0.5, 5.0, 40.0])) * r.standard_normal((b, 2, h, w))).astype(np.float32)
+    flow = oracle.normalize(flow_px).astype(np.float32)
+    ref, ref_mask = oracle.warp(frame, flow, padding_mode=pad, align_corners=ac, return_mask=True)
+    outs = []
+    for variant in (1, 2, 3):
+        out, mask = warp(T(frame), T(flow), padding_mode=pad, align_corners=ac, return_mask=True, variant=variant)
+        assert maxabs(N(out), ref) <= 1e-5, (variant, b, c, h, w, pad, ac)
+        assert np.array_equal(N(mask).astype(np.uint8), ref_mask)
+        outs.append(N(out))
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    fused = warp(T(frame), T(flow_px), padding_mode=pad, align_corners=ac, pixel_flow=True)
+    assert np.array_equal(N(fused), outs[2])
+    # resize to a random size
+    ho, wo = int(r.integers(1, 120)), int(r.integers(1, 260))
+    got = N(resize(T(flow_px), size=(ho, wo)))
+    want = oracle.resize(flow_px, size=(ho, wo))
+    assert maxabs(got, want) <= tol(want), (h, w, ho, wo)
+    # convex upsampling on a coarse grid of the same aspect
+    hc, wc = max(h // 8, 1), max(w // 8, 1)
+    fl = r.standard_normal((b, 2, hc, wc)).astype(np.float32)
+    mk = (2 * r.standard_normal((b, 576, hc, wc))).astype(np.float32)
+    up = N(upsample_flow(T(fl), T(mk)))
+    want = oracle.upsample_flow(fl, mk)
+    assert maxabs(up, want) <= tol(want)
+    # metrics
+    target = (flow_px + r.standard_normal(flow_px.shape)).astype(np.float32)
+    valid = (r.random((b, h, w)) > 0.3).astype(np.float32)
+    m, f1 = AverageEndPointError(), OutlierRatio(abs_threshold=0.5, rel_threshold=0.05)
+    m.update(T(flow_px), T(target), T(valid)); f1.update(T(flow_px), T(target), T(valid))
+    s, n = oracle.epe_sum_count(flow_px, target, valid)
+    so, no = oracle.outlier_sum_count(flow_px, target, valid, 0.5, 0.05)
+    assert int(m.total) == n and abs(float(m._acc[0]) - s) <= 1e-6 * max(1.0, s)
+    assert int(f1.total) == no and float(f1._acc[0]) == so
