@@ -62,7 +62,8 @@ int64_t ofb_launch_count(void);
  *   out   (B,C,H,W) fp32 NCHW
  *   valid_or_null (B,H,W) u8: 1 iff -1 < grid < 1 on both axes -- the predicate of
  *                 bilinear_sampler's mask (methods/raft/model/utils.py:76-78)
- *   variant: 0 = auto, 1 = direct gather, 2 = shared-memory staged neighbourhood, 3 = row kernel
+ *   variant: 0 = auto, 1 = direct gather, 2 = shared-memory staged neighbourhood (cp.async), 3 = row kernel,
+ *            4 = TMA-staged neighbourhood (bilinear NCHW, W % 4 == 0, 16-byte aligned frame; else OFB_EUNSUPPORTED)
  *   flow_mul_x/y: the flow is multiplied by these (one rounded fp32 multiply) before the grid is
  *                 formed: 1, 1 for the reference's normalised flow; 2/max(W-1,1), 2/max(H-1,1) fuses
  *                 optical_flow.normalize (operator.py:117-130) for pixel-unit flows, bit-identically

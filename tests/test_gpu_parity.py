@@ -61,13 +61,20 @@ def test_warp_reference_known_answers():
     assert torch.equal(warp(img, normalize(flow)), torch.tensor([[[2.0], [2.0]]]).unsqueeze(0))
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+def warp_variants(w):
+    """Every bilinear NCHW kernel variant that supports this width (4 = TMA window: 16-byte row strides)."""
+    return (1, 2, 3, 4) if w % 4 == 0 else (1, 2, 3)
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 def test_warp_golden(golden, variant):
     from optical_flow import normalize, warp
 
     g = golden("warp")
     for i in range(int(g["n"])):
         frame, flow_px = T(g[f"frame{i}"]), T(g[f"flow_px{i}"])
+        if variant not in warp_variants(frame.shape[-1]):
+            continue
         flow = normalize(flow_px)
         assert maxabs(N(flow), g[f"flow{i}"]) == 0.0
         out = warp(frame, flow, variant=variant)
@@ -83,7 +90,7 @@ def test_warp_options_golden(golden, mode, pad, ac):
 
     g = golden("warp")
     ref = g[f"opt_{mode}_{pad}_{int(ac)}"]
-    for variant in ([1] if mode == "nearest" else [1, 2, 3]):
+    for variant in ([1] if mode == "nearest" else warp_variants(g["opt_frame"].shape[-1])):
         out = N(warp(T(g["opt_frame"]), T(g["opt_flow"]), mode=mode, padding_mode=pad, align_corners=ac, variant=variant))
         if mode == "nearest":
             assert np.mean(out != ref) <= 0.005
@@ -103,12 +110,12 @@ def test_warp_vs_oracle(shape, sigma, pad, ac):
     flow = oracle.normalize(flow_px).astype(np.float32)
     ref, ref_mask = oracle.warp(frame, flow, padding_mode=pad, align_corners=ac, return_mask=True)
     outs = []
-    for variant in (1, 2, 3):
+    for variant in warp_variants(w):
         out, mask = warp(T(frame), T(flow), padding_mode=pad, align_corners=ac, return_mask=True, variant=variant)
         assert maxabs(N(out), ref) <= 1e-5, variant
         assert np.array_equal(N(mask).astype(np.uint8), ref_mask), variant      # validity mask bit-exact
         outs.append(N(out))
-    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])  # all kernels agree bit for bit
+    assert all(np.array_equal(outs[0], o) for o in outs[1:])                      # all kernels agree bit for bit
     # fused normalize: pixel-unit flow in, same bits out
     fused, fmask = warp(T(frame), T(flow_px), padding_mode=pad, align_corners=ac, return_mask=True, pixel_flow=True)
     assert np.array_equal(N(fused), outs[2]) and np.array_equal(N(fmask).astype(np.uint8), ref_mask)
@@ -143,7 +150,10 @@ def test_warp_full_size_properties():
     o1 = warp(frame, flow, variant=1)
     o2 = warp(frame, flow, variant=2)
     o3 = warp(frame, flow, variant=3)
-    assert torch.equal(o1, o2) and torch.equal(o1, o3)
+    o4 = warp(frame, flow, variant=4)
+    assert torch.equal(o1, o2) and torch.equal(o1, o3) and torch.equal(o1, o4)
+    big = torch.randn((b, 2, h, w), device="cuda", generator=gen) * 0.05   # +-25 px: most taps leave the TMA window
+    assert torch.equal(warp(frame, big, variant=3), warp(frame, big, variant=4))
     frame2 = torch.rand((b, c, h, w), device="cuda", generator=gen)
     lin = warp(frame + frame2, flow)
     assert float((lin - (o1 + warp(frame2, flow))).abs().max()) <= 4e-6
@@ -700,10 +710,10 @@ def test_kernels_do_not_write_outside_their_buffers():
                     assert intact(whole, n, -7.0), (b, c, h, w, mode, cg)
                 assert intact(whole_o, n_out, -7.0) and bool(torch.isfinite(out).all())
     # streaming kernels at odd sizes
-    for (b, c, h, w) in [(2, 3, 37, 53), (1, 5, 16, 130)]:
+    for (b, c, h, w) in [(2, 3, 37, 53), (1, 5, 16, 130), (2, 6, 19, 132)]:
         frame = torch.rand((b, c, h, w), device="cuda", generator=gen)
         flow = torch.randn((b, 2, h, w), device="cuda", generator=gen) * 0.3
-        for variant in (1, 2, 3):
+        for variant in warp_variants(w):
             whole, out = banded(b * c * h * w, torch.float32, -7.0)
             wm, mask = banded(b * h * w, torch.uint8, 200)
             ofb200.check(lib.ofb_warp_f32(ofb200.ptr(frame), ofb200.ptr(flow), ofb200.ptr(out), ofb200.ptr(mask), b, c, h, w,
@@ -765,6 +775,8 @@ def test_random_shapes_streaming_kernels(seed):
     r = rng(2000 + seed)
     b, c = int(r.integers(1, 4)), int(r.integers(1, 6))
     h, w = int(r.integers(2, 90)), int(r.integers(2, 200))
+    if seed % 2:
+        w = (w + 3) // 4 * 4                                  # widths the TMA-window warp accepts
     pad = str(r.choice(["zeros", "border", "reflection"]))
     ac = bool(r.integers(0, 2))
     frame = r.random((b, c, h, w), dtype=np.float32)
@@ -772,12 +784,12 @@ def test_random_shapes_streaming_kernels(seed):
     flow = oracle.normalize(flow_px).astype(np.float32)
     ref, ref_mask = oracle.warp(frame, flow, padding_mode=pad, align_corners=ac, return_mask=True)
     outs = []
-    for variant in (1, 2, 3):
+    for variant in warp_variants(w):
         out, mask = warp(T(frame), T(flow), padding_mode=pad, align_corners=ac, return_mask=True, variant=variant)
         assert maxabs(N(out), ref) <= 1e-5, (variant, b, c, h, w, pad, ac)
         assert np.array_equal(N(mask).astype(np.uint8), ref_mask)
         outs.append(N(out))
-    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    assert all(np.array_equal(outs[0], o) for o in outs[1:])
     fused = warp(T(frame), T(flow_px), padding_mode=pad, align_corners=ac, pixel_flow=True)
     assert np.array_equal(N(fused), outs[2])
     # resize to a random size

@@ -53,8 +53,8 @@ def record(name, ms, nbytes=None, flops=None, **extra):
     return rec
 
 
-def smooth_flow(b, h, w, sigma, gen):
-    low = torch.randn((b, 2, h // 16 + 2, w // 16 + 2), device="cuda", generator=gen) * sigma
+def smooth_flow(b, h, w, sigma, gen, spacing=16):
+    low = torch.randn((b, 2, h // spacing + 2, w // spacing + 2), device="cuda", generator=gen) * sigma
     return torch.nn.functional.interpolate(low, size=(h, w), mode="bilinear", align_corners=True).contiguous()
 
 
@@ -64,7 +64,10 @@ def bench_warp_c2(variants=(0,), flows=("white5px", "smooth5px"), masks=(1,)):
     gen = torch.Generator(device="cuda").manual_seed(1234)
     frames = [torch.rand((b, c, h, w), device="cuda", generator=gen) for _ in range(2)]
     mk = {"white5px": lambda: normalize(5 * torch.randn((b, 2, h, w), device="cuda", generator=gen)),
-          "smooth5px": lambda: normalize(smooth_flow(b, h, w, 5.0, gen))}
+          "smooth5px": lambda: normalize(smooth_flow(b, h, w, 5.0, gen)),
+          # control points every 64 px: gradients <= ~0.1 px/px, the regime of real flow fields away from motion edges
+          "smooth5px64": lambda: normalize(smooth_flow(b, h, w, 5.0, gen, 64)),
+          "smooth20px64": lambda: normalize(smooth_flow(b, h, w, 20.0, gen, 64))}
     px = b * h * w
     lib = ofb200.load()
     out = torch.empty_like(frames[0])

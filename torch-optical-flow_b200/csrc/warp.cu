@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(NT) warp_staged_kernel(const float* __restrict
 // thread walks RPT consecutive rows of its column: the lower taps of row i are the upper taps of row i+1 for
 // smooth flows, so they hit L1.  The coordinate pipeline and the 4 tap offsets are computed once per pixel
 // and reused for every channel.
-constexpr int RPT_DEFAULT = 4;   // rows per thread
+constexpr int RPT_DEFAULT = 2;   // rows per thread: 32 registers, 64 resident warps per SM (see the sweep in DESIGN.md)
 
 template <int PAD, bool AC, int RPT>
 __global__ void __launch_bounds__(128) warp_rows_kernel(const float* __restrict__ frame, const float* __restrict__ flow,
@@ -317,6 +317,32 @@ __global__ void __launch_bounds__(128) warp_rows_kernel(const float* __restrict_
         inb |= (((iny0 && inx0) ? 1u : 0u) | ((iny0 && inx1) ? 2u : 0u) | ((iny1 && inx0) ? 4u : 0u) |
                 ((iny1 && inx1) ? 8u : 0u)) << (4 * k);
         o00[k] = y0 * W + x0;
+    }
+    // interior pixels (all 4 x RPT taps inside the frame -- everything but the last row / column and, under zeros
+    // padding, samples that leave the frame): no predicates, no per-tap address arithmetic.  The kernel is bound
+    // by instruction issue, not by HBM, so the channel loop is kept to 4 loads + 4 FMAs + 1 store per pixel.
+    if (inb == (RPT == 8 ? 0xFFFFFFFFu : (1u << (4 * RPT)) - 1u)) {
+        const float* plane = frame + (size_t)(b * C) * HW;
+        float* op = out + (size_t)(b * C) * HW + i0 * W + j;
+#pragma unroll 1
+        for (int c = 0; c < C; ++c, plane += HW, op += HW) {
+            float v[RPT][4];                              // all 4 x RPT gathers in flight before the first FMA
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) {
+                const float* p = plane + o00[k];
+                const float* q = p + W;
+                v[k][0] = __ldg(p); v[k][1] = __ldg(p + 1); v[k][2] = __ldg(q); v[k][3] = __ldg(q + 1);
+            }
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) {
+                float acc = __fmaf_rn(v[k][0], w00[k], 0.0f);
+                acc = __fmaf_rn(v[k][1], w01[k], acc);
+                acc = __fmaf_rn(v[k][2], w10[k], acc);
+                acc = __fmaf_rn(v[k][3], w11[k], acc);
+                op[k * W] = acc;
+            }
+        }
+        return;
     }
     for (int c = 0; c < C; ++c) {
         const float* plane = frame + (size_t)(b * C + c) * HW;
@@ -372,12 +398,15 @@ int launch_rows(const float* frame, const float* flow, float* out, uint8_t* vali
     if (!rpt) {
         const char* e = getenv("OFB_WARP_RPT");           // tuning override
         rpt = e ? atoi(e) : RPT_DEFAULT;
-        if (rpt != 2 && rpt != 4 && rpt != 8) rpt = RPT_DEFAULT;
+        if (rpt != 1 && rpt != 2 && rpt != 4 && rpt != 8) rpt = RPT_DEFAULT;
     }
-    dim3 grid((W + 127) / 128, (H + rpt - 1) / rpt, B);
-    if (rpt == 2) warp_rows_kernel<PAD, AC, 2><<<grid, 128, 0, st>>>(frame, flow, out, valid, C, H, W, fm);
-    else if (rpt == 8) warp_rows_kernel<PAD, AC, 8><<<grid, 128, 0, st>>>(frame, flow, out, valid, C, H, W, fm);
-    else warp_rows_kernel<PAD, AC, 4><<<grid, 128, 0, st>>>(frame, flow, out, valid, C, H, W, fm);
+    const dim3 block(128);
+    const dim3 grid((W + 127) / 128, (H + rpt - 1) / rpt, B);
+    if (grid.y > 65535) return OFB_EUNSUPPORTED;
+    if (rpt == 1) warp_rows_kernel<PAD, AC, 1><<<grid, block, 0, st>>>(frame, flow, out, valid, C, H, W, fm);
+    else if (rpt == 2) warp_rows_kernel<PAD, AC, 2><<<grid, block, 0, st>>>(frame, flow, out, valid, C, H, W, fm);
+    else if (rpt == 8) warp_rows_kernel<PAD, AC, 8><<<grid, block, 0, st>>>(frame, flow, out, valid, C, H, W, fm);
+    else warp_rows_kernel<PAD, AC, 4><<<grid, block, 0, st>>>(frame, flow, out, valid, C, H, W, fm);
     OFB_LAUNCH_CHECK();
     return OFB_OK;
 }
@@ -434,21 +463,37 @@ int dispatch_staged(int pad, int ac, int rows, const float* frame, const float* 
 
 }  // namespace
 
+// warp_tma.cu
+int ofb_warp_tma_launch(const float* frame, const float* flow, float* out, uint8_t* valid, int B, int C, int H, int W,
+                        int pad, int ac, float fmx, float fmy, cudaStream_t st);
+
 OFB_API int ofb_warp_f32(const float* frame, const float* flow, float* out, uint8_t* valid_or_null, int B, int C, int H,
                          int W, int mode, int padding_mode, int align_corners, int channels_last, int variant,
                          float flow_mul_x, float flow_mul_y, void* stream) {
     if (!frame || !flow || !out || B < 0 || C < 0 || H < 0 || W < 0) return OFB_EINVAL;
     if (mode != OFB_MODE_BILINEAR && mode != OFB_MODE_NEAREST) return OFB_EINVAL;
-    if (padding_mode < 0 || padding_mode > 2 || variant < 0 || variant > 3) return OFB_EINVAL;
+    if (padding_mode < 0 || padding_mode > 2 || variant < 0 || variant > 4) return OFB_EINVAL;
     if ((size_t)B * C * H * W == 0) return OFB_OK;
     if (B > 65535) return OFB_EUNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     const FlowMul fm{flow_mul_x, flow_mul_y};
     const bool nchw_bilinear = mode == OFB_MODE_BILINEAR && !channels_last;
-    const bool can_rows = nchw_bilinear && H <= 65535 * 2 && (long long)H * W < (1LL << 30) && (long long)B * C * H * W < (1LL << 40);
-    if ((variant == 2 && !nchw_bilinear) || (variant == 3 && !can_rows)) return OFB_EUNSUPPORTED;
-    // auto: the row kernel; 1 = direct gather (also nearest / NHWC), 2 = shared-memory staged, 3 = row kernel
-    const int v = variant != 0 ? variant : (can_rows ? 3 : 1);
+    const bool can_rows = nchw_bilinear && H <= 65535 * RPT_DEFAULT && (long long)H * W < (1LL << 30) && (long long)B * C * H * W < (1LL << 40);
+    // TMA needs 16-byte global strides
+    const bool can_tma = can_rows && W % 4 == 0 && (reinterpret_cast<uintptr_t>(frame) & 15) == 0 &&
+                         (long long)B * C < (1LL << 31);
+    if ((variant == 2 && !nchw_bilinear) || (variant == 3 && !can_rows) || (variant == 4 && !can_tma))
+        return OFB_EUNSUPPORTED;
+    // auto: the row kernel; 1 = direct gather (also nearest / NHWC), 2 = cp.async-staged, 3 = row kernel,
+    // 4 = TMA-staged window (warp_tma.cu)
+    static int auto_v = -1;
+    if (auto_v < 0) {
+        const char* e = getenv("OFB_WARP_VARIANT");       // tuning override for variant 0
+        auto_v = e ? atoi(e) : 0;
+    }
+    int v = variant != 0 ? variant : (auto_v == 4 && can_tma ? 4 : (can_rows ? 3 : 1));
+    if (v == 4)
+        return ofb_warp_tma_launch(frame, flow, out, valid_or_null, B, C, H, W, padding_mode, align_corners, fm.x, fm.y, st);
     if (v == 2 || v == 3)
         return dispatch_staged(padding_mode, align_corners, v == 3, frame, flow, out, valid_or_null, B, C, H, W, fm, st);
     if (mode == OFB_MODE_BILINEAR)

@@ -50,7 +50,7 @@ def warp(
         return_mask: extension (default off): also return the (B, H, W) bool validity mask -- the
             predicate of ``bilinear_sampler(mask=True)`` (reference methods/raft/model/utils.py:76-78)
             evaluated on the warp grid: True where the source position lies strictly inside the frame
-        variant: kernel selection, 0 = auto, 1 = direct gather, 2 = shared-memory staged, 3 = row kernel
+        variant: kernel selection, 0 = auto, 1 = direct gather, 2 = cp.async-staged, 3 = row kernel, 4 = TMA-staged
         pixel_flow: extension (default off): `flow` is in pixel units and :func:`normalize` is fused into
             the kernel -- ``warp(f, flow, pixel_flow=True)`` equals ``warp(f, normalize(flow))`` bit for bit
 
