@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define OFB_VERSION 110
+#define OFB_VERSION 120
 
 #define OFB_OK 0
 #define OFB_EINVAL (-1)       /* bad size / null pointer / unsupported enum value          */
@@ -114,6 +114,18 @@ int ofb_epe_map_f32(const float* pred, const float* target, float* out, int B, i
 int ofb_outlier_reduce_f32(const float* pred, const float* target, const float* valid_or_null,
                            double* acc, int B, int H, int W, float abs_threshold, float rel_threshold,
                            void* stream);
+/* sequence_loss (methods/raft/model/raft.py:231-260), forward value, one fused pass:
+ *   keep = (valid >= 0.5) & (|flow_gt|_2 < max_flow)
+ *   acc[0] += sum_i gamma^(n-1-i) * sum(keep * |preds[i] - flow_gt|)   -> loss = acc[0] / (B*2*H*W)
+ *   acc[1] += sum of the end-point error of preds[n-1] over kept pixels
+ *   acc[2] += number of kept pixels; acc[3..5] += kept pixels with that error < 1, < 3, < 5 px
+ *             -> the reference's "1px" / "3px" / "5px" metrics = acc[3..5] / acc[2]
+ * preds: HOST array of n_predictions device pointers, each (B,2,H,W) fp32; n_predictions <=
+ * OFB_MAX_PREDICTIONS; acc: 6 device doubles, accumulated (zero them first). */
+#define OFB_MAX_PREDICTIONS 24
+int ofb_sequence_loss_f32(const float* const* preds, int n_predictions, const float* flow_gt,
+                          const float* valid, double* acc, int B, int H, int W, double gamma,
+                          float max_flow, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Correlation pyramid layout (owned by the caller, described by ofb_pyramid_layout).

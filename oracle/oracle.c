@@ -413,6 +413,40 @@ ORC_API void orc_outlier_f32(const float* pred, const float* target, const float
     *count_out = cnt;
 }
 
+/* sequence_loss (methods/raft/model/raft.py:231-260): keep = (valid >= 0.5) & (|gt| < max_flow);
+ * loss = sum_i gamma^(n-1-i) * mean(keep * |pred_i - gt|) over all B*2*H*W elements; the metrics are the fractions
+ * of kept pixels whose end-point error of the last prediction is below 1 / 3 / 5 px.
+ * out[0] = loss, out[1] = sum of kept epe, out[2] = kept count, out[3..5] = counts below 1 / 3 / 5 px. */
+ORC_API void orc_sequence_loss_f32(const float* const* preds, int n, const float* gt, const float* valid, double* out,
+                                   int B, int H, int W, double gamma, float max_flow) {
+    const size_t HW = (size_t)H * W;
+    double loss = 0.0, epe = 0.0;
+    int64_t keep = 0, n1 = 0, n3 = 0, n5 = 0;
+    for (int i = 0; i < n; ++i) {
+        double w = 1.0;
+        for (int k = 0; k < n - 1 - i; ++k) w *= gamma;
+        double total = 0.0;
+        const float* pred = preds[i];
+        const int last = (i == n - 1);
+#pragma omp parallel for reduction(+ : total, epe, keep, n1, n3, n5) schedule(static)
+        for (int64_t q = 0; q < (int64_t)B * (int64_t)HW; ++q) {
+            size_t b = (size_t)q / HW, p = (size_t)q % HW;
+            float gx = gt[(b * 2 + 0) * HW + p], gy = gt[(b * 2 + 1) * HW + p];
+            float mag = sqrtf(gx * gx + gy * gy);
+            float m = (valid[q] >= 0.5f && mag < max_flow) ? 1.0f : 0.0f;
+            float dx = pred[(b * 2 + 0) * HW + p] - gx, dy = pred[(b * 2 + 1) * HW + p] - gy;
+            total += (double)(m * fabsf(dx)) + (double)(m * fabsf(dy));
+            if (last && m != 0.0f) {
+                float e = sqrtf(dx * dx + dy * dy);
+                epe += (double)e;
+                keep += 1; n1 += e < 1.0f; n3 += e < 3.0f; n5 += e < 5.0f;
+            }
+        }
+        loss += w * (total / ((double)B * 2.0 * (double)HW));
+    }
+    out[0] = loss; out[1] = epe; out[2] = (double)keep; out[3] = (double)n1; out[4] = (double)n3; out[5] = (double)n5;
+}
+
 /* Per-pixel EPE map (end_point_error(reduce=False), epe.py:41-61). */
 ORC_API void orc_epe_map_f32(const float* pred, const float* target, float* out, int B, int H, int W) {
     const size_t HW = (size_t)H * W;

@@ -16,6 +16,7 @@ Every function mirrors one reference entry point (paths relative to /root/refere
     upsample_flow     methods/raft/model/raft.py:73-85
     end_point_error / epe_sum_count   optical_flow/metrics/epe.py:25-61
     outlier_sum_count  optical_flow/metrics/f1.py:33-48
+    sequence_loss      methods/raft/model/raft.py:231-260
 
 All arrays are C-contiguous float32 numpy arrays in the reference's layouts (NCHW).
 """
@@ -62,7 +63,7 @@ _lib = _load()
 for _n in (
     "orc_linspace_f32", "orc_grid_sample_f32", "orc_warp_f32", "orc_resize_bilinear_f32",
     "orc_avg_pool2_f32", "orc_corr_lookup_f32", "orc_convex_upsample_f32", "orc_epe_f32",
-    "orc_epe_map_f32", "orc_round_bf16_f32", "orc_outlier_f32",
+    "orc_epe_map_f32", "orc_round_bf16_f32", "orc_outlier_f32", "orc_sequence_loss_f32",
 ):
     getattr(_lib, _n).restype = None
 _lib.orc_linspace_f32.argtypes = [ctypes.c_float, ctypes.c_float, ctypes.c_int, _c_f]
@@ -80,6 +81,8 @@ _lib.orc_epe_f32.argtypes = [_c_f, _c_f, _c_f, ctypes.POINTER(ctypes.c_double),
 _lib.orc_epe_map_f32.argtypes = [_c_f, _c_f, _c_f] + [ctypes.c_int] * 3
 _lib.orc_outlier_f32.argtypes = [_c_f, _c_f, _c_f, ctypes.POINTER(ctypes.c_double),
                                  ctypes.POINTER(ctypes.c_int64)] + [ctypes.c_int] * 3 + [ctypes.c_float] * 2
+_lib.orc_sequence_loss_f32.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, _c_f, _c_f,
+                                       ctypes.POINTER(ctypes.c_double)] + [ctypes.c_int] * 3 + [ctypes.c_double, ctypes.c_float]
 _lib.orc_round_bf16_f32.argtypes = [_c_f, _c_f, ctypes.c_int64]
 
 _MODES = {"bilinear": 0, "nearest": 1}
@@ -296,6 +299,20 @@ def outlier_sum_count(pred, target, valid=None, abs_threshold=3.0, rel_threshold
     _lib.orc_outlier_f32(_p(pred), _p(target), _p(v) if v is not None else None, ctypes.byref(s), ctypes.byref(c),
                          b, h, w, abs_threshold, rel_threshold)
     return s.value, c.value
+
+
+def sequence_loss(flow_preds, flow_gt, valid, gamma=0.8, max_flow=400.0):
+    """methods/raft/model/raft.py:231-260 -> (loss, {"1px", "3px", "5px"}, extras {"epe_sum", "kept"})."""
+    preds = [_f32(p) for p in flow_preds]
+    gt, v = _f32(flow_gt), _f32(valid)
+    b, two, h, w = gt.shape
+    assert two == 2 and v.shape == (b, h, w) and all(p.shape == gt.shape for p in preds)
+    arr = (ctypes.c_void_p * len(preds))(*[p.ctypes.data for p in preds])
+    out = (ctypes.c_double * 6)()
+    _lib.orc_sequence_loss_f32(arr, len(preds), _p(gt), _p(v), out, b, h, w, float(gamma), float(max_flow))
+    kept = out[2]
+    metrics = {k: (out[i] / kept if kept > 0 else float("nan")) for k, i in (("1px", 3), ("3px", 4), ("5px", 5))}
+    return out[0], metrics, {"epe_sum": out[1], "kept": int(kept)}
 
 
 def end_point_error(pred, target, reduce=True):

@@ -84,3 +84,15 @@ def epe_sum_count(pred, target, valid=None):
     if valid is not None:
         epe = epe[valid.view(-1) >= 0.5]
     return float(epe.sum()), int(epe.numel())
+
+
+def sequence_loss(flow_preds, flow_gt, valid, gamma=0.8, max_flow=400.0):
+    """methods/raft/model/raft.py:231-260 -- gamma-weighted masked L1 over the prediction sequence, plus the
+    fractions of kept pixels whose final end-point error is below 1 / 3 / 5 px."""
+    n = len(flow_preds)
+    keep = (valid >= 0.5) & (torch.sum(flow_gt ** 2, dim=1).sqrt() < max_flow)
+    loss = 0.0
+    for i, pred in enumerate(flow_preds):
+        loss = loss + gamma ** (n - i - 1) * (keep[:, None] * (pred - flow_gt).abs()).mean()
+    epe = torch.sum((flow_preds[-1] - flow_gt) ** 2, dim=1).sqrt().view(-1)[keep.view(-1)]
+    return loss, {f"{t}px": (epe < t).float().mean().item() for t in (1, 3, 5)}

@@ -216,6 +216,23 @@ def make_upsample_epe():
     save("upsample_epe", ref_call="RAFT.upsample_flow; optical_flow.metrics.epe.end_point_error / AverageEndPointError", **cases)
 
 
+# ------------------------------------------------------ sequence_loss (raft.py:231-260)
+def make_sequence_loss():
+    from model.raft import sequence_loss
+
+    cases = {}
+    gt = 6.0 * torch.randn(2, 2, 20, 28, generator=g(80))
+    gt[0, :, 3, 4] = 500.0                                   # |gt| >= max_flow: dropped
+    valid = (torch.rand(2, 20, 28, generator=g(81)) > 0.25).float()
+    preds = [gt + (3.0 / (i + 1)) * torch.randn(2, 2, 20, 28, generator=g(82 + i)) for i in range(5)]
+    loss, metrics = sequence_loss(preds, gt, valid)
+    cases.update(gt=gt, valid=valid, preds=torch.stack(preds), loss=loss,
+                 m=torch.tensor([metrics["1px"], metrics["3px"], metrics["5px"]], dtype=torch.float64))
+    loss2, metrics2 = sequence_loss(preds[:1], gt, valid, gamma=0.5, max_flow=10.0)
+    cases.update(loss2=loss2, m2=torch.tensor([metrics2["1px"], metrics2["3px"], metrics2["5px"]], dtype=torch.float64))
+    save("sequence_loss", ref_call="model.raft.sequence_loss(flow_preds, flow_gt, valid, gamma, max_flow)", **cases)
+
+
 # ------------------------------------------------------ RAFT.forward trace (raft.py:87-147)
 def make_raft_trace():
     """Run the UNMODIFIED reference RAFT (random weights, eval mode) on one small image pair and record
@@ -265,8 +282,12 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["raft_trace"]:
         make_raft_trace()
         sys.exit(0)
+    if sys.argv[1:] == ["sequence_loss"]:
+        make_sequence_loss()
+        sys.exit(0)
     make_warp()
     make_resize()
     make_corr()
     make_upsample_epe()
+    make_sequence_loss()
     make_raft_trace()

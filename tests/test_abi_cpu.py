@@ -30,7 +30,7 @@ def test_every_header_symbol_is_exported_and_bound(lib):
     for s in syms:
         assert hasattr(raw, s), f"{s} declared in include/ofb200.h but not exported"
         assert s in ofb200.SIGNATURES, f"{s} has no ctypes signature"
-    assert lib.ofb_version() == 110
+    assert lib.ofb_version() == 120
     assert lib.ofb_strerror(0) == b"ok"
     assert b"invalid" in lib.ofb_strerror(-1)
 

@@ -330,6 +330,43 @@ def test_outlier_ratio_golden_and_oracle(golden):
     assert float(m._acc[0]) == s and int(m.total) == n
 
 
+def test_sequence_loss_golden_and_oracle(golden):
+    """sequence_loss (reference methods/raft/model/raft.py:231-260) as one fused reduction: the reference's own
+    outputs, then a 12-prediction KITTI-size case against the oracle (counts exact, loss to 1e-6 relative), a
+    non-vectorisable size, host tensors and the error paths."""
+    from model import sequence_loss
+
+    g = golden("sequence_loss")
+    preds = [T(g["preds"][i]) for i in range(g["preds"].shape[0])]
+    loss, m = sequence_loss(preds, T(g["gt"]), T(g["valid"]))
+    assert loss.is_cuda and loss.dtype == torch.float32 and loss.dim() == 0
+    assert abs(float(loss) - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
+    assert [m["1px"], m["3px"], m["5px"]] == pytest.approx(list(g["m"]), abs=1e-7)
+    loss2, m2 = sequence_loss(preds[:1], T(g["gt"]), T(g["valid"]), gamma=0.5, max_flow=10.0)
+    assert abs(float(loss2) - float(g["loss2"])) <= 1e-5 * abs(float(g["loss2"]))
+    assert [m2["1px"], m2["3px"], m2["5px"]] == pytest.approx(list(g["m2"]), abs=1e-7)
+    host_loss, host_m = sequence_loss([p.cpu() for p in preds], T(g["gt"]).cpu(), T(g["valid"]).cpu())
+    assert not host_loss.is_cuda and float(host_loss) == float(loss) and host_m == m
+
+    r = rng(23)
+    for (b, h, w, n) in [(2, 376, 1248, 12), (3, 11, 17, 3), (1, 5, 7, 24)]:
+        gt = (8 * r.standard_normal((b, 2, h, w))).astype(np.float32)
+        gt[0, :, 0, 0] = 1000.0
+        valid = (r.random((b, h, w)) > 0.3).astype(np.float32)
+        ps = [(gt + (4.0 / (i + 1)) * r.standard_normal(gt.shape)).astype(np.float32) for i in range(n)]
+        want, wm, extra = oracle.sequence_loss(ps, gt, valid, gamma=0.85, max_flow=400.0)
+        got, gm = sequence_loss([T(p) for p in ps], T(gt), T(valid), gamma=0.85, max_flow=400.0)
+        assert abs(float(got) - want) <= 1e-6 * abs(want), (b, h, w, n)
+        assert gm == pytest.approx(wm, abs=1e-12), (b, h, w, n)                     # ratios of exact counts
+    # nothing kept: the reference's mean() of an empty selection is NaN
+    _, em = sequence_loss([T(ps[0])], T(gt), T(np.zeros_like(valid)))
+    assert all(np.isnan(v) for v in em.values())
+    with pytest.raises(NotImplementedError):
+        sequence_loss([T(ps[0])] * 25, T(gt), T(valid))
+    with pytest.raises(RuntimeError):
+        sequence_loss([T(ps[0])[:, :, :-1]], T(gt), T(valid))
+
+
 @pytest.mark.parametrize("shape", [(16, 376, 1248), (3, 11, 17), (2, 1088, 1920)])
 def test_epe_vs_oracle(shape):
     from optical_flow.metrics import AverageEndPointError

@@ -155,6 +155,26 @@ def bench_lookup_c4():
     return recs
 
 
+def bench_sequence_loss_c4(n_pred=12):
+    """sequence_loss over 12 full-resolution predictions at the C4 (KITTI) size: 8 B/px per prediction + 12 B/px."""
+    import ctypes
+    n, h, w = 16, 376, 1248
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    gt = 8 * torch.randn((n, 2, h, w), device="cuda", generator=gen)
+    valid = (torch.rand((n, h, w), device="cuda", generator=gen) > 0.1).float()
+    preds = [gt + torch.randn((n, 2, h, w), device="cuda", generator=gen) for _ in range(n_pred)]
+    acc = torch.zeros(6, dtype=torch.float64, device="cuda")
+    ptrs = (ctypes.c_void_p * n_pred)(*[p.data_ptr() for p in preds])
+    lib = ofb200.load()
+
+    def run():
+        rc = lib.ofb_sequence_loss_f32(ptrs, n_pred, ofb200.ptr(gt), ofb200.ptr(valid), ofb200.ptr(acc), n, h, w, 0.8, 400.0,
+                                       ofb200.stream_ptr())
+        assert rc == 0
+    ms = timeit(run)
+    return [record(f"C4 B16 376x1248 K4d sequence_loss x{n_pred} predictions", ms, nbytes=n * h * w * (8 * n_pred + 12))]
+
+
 def bench_upsample_c4(epe=True, upflow=True):
     n, h, w = 16, 47, 156
     gen = torch.Generator(device="cuda").manual_seed(3)

@@ -87,6 +87,94 @@ __global__ void __launch_bounds__(NT) epe_map_kernel(const float* __restrict__ p
     }
 }
 
+
+// ---------------------------------------------------------------------------------- sequence loss
+// sequence_loss (reference methods/raft/model/raft.py:231-260) in one pass over the ground truth:
+//   keep = (valid >= 0.5) & (|gt| < max_flow)
+//   loss = sum_i gamma^(n-1-i) * mean(keep * |pred_i - gt|)     (mean over ALL B*2*H*W elements)
+//   epe  = |pred_{n-1} - gt|_2 over kept pixels -> fractions below 1 / 3 / 5 px
+// The reference makes 4 elementwise passes per prediction plus the metric passes; here the ground truth and
+// validity map are read once and every prediction once (8 bytes per pixel per prediction).
+constexpr int MAX_PREDS = OFB_MAX_PREDICTIONS;
+struct PredList {
+    const float* p[MAX_PREDS];
+    double w[MAX_PREDS];
+};
+
+struct SeqAcc {
+    double loss, epe;
+    unsigned long long keep, n1, n3, n5;
+};
+
+__global__ void __launch_bounds__(NT) sequence_loss_kernel(const __grid_constant__ PredList preds, int n,
+                                                           const float* __restrict__ gt, const float* __restrict__ valid,
+                                                           double* __restrict__ acc, int B, int64_t HW, int vec,
+                                                           float max_flow) {
+    SeqAcc a{0.0, 0.0, 0ull, 0ull, 0ull, 0ull};
+    const int64_t step = vec ? 4 : 1;
+    const int64_t per_b = HW / step;
+    const int64_t total = (int64_t)B * per_b;
+    for (int64_t t = (int64_t)blockIdx.x * NT + threadIdx.x; t < total; t += (int64_t)gridDim.x * NT) {
+        const int64_t b = t / per_b, q = (t - b * per_b) * step;
+        const int64_t ox = (b * 2 + 0) * HW + q, oy = (b * 2 + 1) * HW + q, ov = b * HW + q;
+        float gx[4], gy[4], m[4];
+        if (vec) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(gt + ox)), y = __ldg(reinterpret_cast<const float4*>(gt + oy));
+            const float4 v = __ldg(reinterpret_cast<const float4*>(valid + ov));
+            gx[0] = x.x; gx[1] = x.y; gx[2] = x.z; gx[3] = x.w;
+            gy[0] = y.x; gy[1] = y.y; gy[2] = y.z; gy[3] = y.w;
+            m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w;
+        } else {
+            gx[0] = __ldg(gt + ox); gy[0] = __ldg(gt + oy); m[0] = __ldg(valid + ov);
+        }
+        const int cnt = vec ? 4 : 1;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (k >= cnt) break;
+            const float mag = sqrtf(__fadd_rn(__fmul_rn(gx[k], gx[k]), __fmul_rn(gy[k], gy[k])));
+            m[k] = (m[k] >= 0.5f && mag < max_flow) ? 1.0f : 0.0f;
+            a.keep += m[k] != 0.0f;
+        }
+        for (int i = 0; i < n; ++i) {
+            float px[4], py[4];
+            if (vec) {
+                const float4 x = __ldg(reinterpret_cast<const float4*>(preds.p[i] + ox));
+                const float4 y = __ldg(reinterpret_cast<const float4*>(preds.p[i] + oy));
+                px[0] = x.x; px[1] = x.y; px[2] = x.z; px[3] = x.w;
+                py[0] = y.x; py[1] = y.y; py[2] = y.z; py[3] = y.w;
+            } else {
+                px[0] = __ldg(preds.p[i] + ox); py[0] = __ldg(preds.p[i] + oy);
+            }
+            float part = 0.0f;                            // keep * |d|: a NaN under a dropped pixel stays NaN, as there
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (k >= cnt) break;
+                const float dx = __fsub_rn(px[k], gx[k]), dy = __fsub_rn(py[k], gy[k]);
+                part += __fmul_rn(m[k], fabsf(dx)) + __fmul_rn(m[k], fabsf(dy));
+                if (i == n - 1 && m[k] != 0.0f) {
+                    const float e = sqrtf(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+                    a.epe += (double)e;
+                    a.n1 += e < 1.0f; a.n3 += e < 3.0f; a.n5 += e < 5.0f;
+                }
+            }
+            a.loss += preds.w[i] * (double)part;
+        }
+    }
+    __shared__ double s_red[NT / 32][6];
+    double v[6] = {a.loss, a.epe, (double)a.keep, (double)a.n1, (double)a.n3, (double)a.n5};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) v[k] = ofb::warp_sum(v[k]);
+    if ((threadIdx.x & 31) == 0)
+        for (int k = 0; k < 6; ++k) s_red[threadIdx.x >> 5][k] = v[k];
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double tsum = 0.0;
+#pragma unroll
+        for (int wv = 0; wv < NT / 32; ++wv) tsum += s_red[wv][threadIdx.x];
+        atomicAdd(acc + threadIdx.x, tsum);
+    }
+}
+
 }  // namespace
 
 namespace {
@@ -128,6 +216,34 @@ OFB_API int ofb_epe_map_f32(const float* pred, const float* target, float* out, 
     const int cap = ofb_num_sms() * 32;
     if (blocks > cap) blocks = cap;
     epe_map_kernel<<<(int)blocks, NT, 0, (cudaStream_t)stream>>>(pred, target, out, B, HW);
+    OFB_LAUNCH_CHECK();
+    return OFB_OK;
+}
+
+OFB_API int ofb_sequence_loss_f32(const float* const* preds, int n_predictions, const float* flow_gt, const float* valid,
+                                  double* acc, int B, int H, int W, double gamma, float max_flow, void* stream) {
+    if (!preds || !flow_gt || !valid || !acc || B < 0 || H < 0 || W < 0 || n_predictions < 1) return OFB_EINVAL;
+    if (n_predictions > MAX_PREDS) return OFB_EUNSUPPORTED;
+    const int64_t HW = (int64_t)H * W;
+    if ((int64_t)B * HW == 0) return OFB_OK;
+    PredList pl;
+    uintptr_t al = reinterpret_cast<uintptr_t>(flow_gt) | reinterpret_cast<uintptr_t>(valid);
+    for (int i = 0; i < MAX_PREDS; ++i) { pl.p[i] = nullptr; pl.w[i] = 0.0; }
+    double wgt = 1.0;                                     // gamma ** (n - 1 - i), as the reference's Python float
+    for (int i = n_predictions - 1; i >= 0; --i) {
+        if (!preds[i]) return OFB_EINVAL;
+        pl.p[i] = preds[i];
+        pl.w[i] = wgt;
+        wgt *= gamma;
+        al |= reinterpret_cast<uintptr_t>(preds[i]);
+    }
+    const int vec = (HW % 4 == 0) && ((al & 15) == 0);
+    const int64_t work = vec ? (int64_t)B * (HW / 4) : (int64_t)B * HW;
+    int64_t blocks = (work + NT - 1) / NT;
+    const int cap = ofb_num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    sequence_loss_kernel<<<(int)blocks, NT, 0, (cudaStream_t)stream>>>(pl, n_predictions, flow_gt, valid, acc, B, HW, vec,
+                                                                      max_flow);
     OFB_LAUNCH_CHECK();
     return OFB_OK;
 }

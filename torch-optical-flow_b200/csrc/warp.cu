@@ -32,6 +32,7 @@ struct SrcPos {
 // optical_flow.normalize (operator.py:117-130) into the warp -- one separately rounded multiply, as there
 struct FlowMul {
     float x, y;
+    float step_x, step_y;   // linspace(-1, 1, W / H) steps, divided once on the host (same IEEE fp32 division)
 };
 
 template <int PAD, bool AC>
@@ -282,7 +283,7 @@ __global__ void __launch_bounds__(128) warp_rows_kernel(const float* __restrict_
     const int i0 = blockIdx.y * RPT;
     if (j >= W) return;
     const int HW = H * W;                                     // launch guard: H*W < 2^30
-    const float step_x = linspace_step(W), step_y = linspace_step(H);
+    const float step_x = fm.step_x, step_y = fm.step_y;
     const float* fxp = flow + (size_t)(b * 2) * HW;
     const float* fyp = fxp + HW;
     int o00[RPT];
@@ -476,7 +477,7 @@ OFB_API int ofb_warp_f32(const float* frame, const float* flow, float* out, uint
     if ((size_t)B * C * H * W == 0) return OFB_OK;
     if (B > 65535) return OFB_EUNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
-    const FlowMul fm{flow_mul_x, flow_mul_y};
+    const FlowMul fm{flow_mul_x, flow_mul_y, ofb::linspace_step(W), ofb::linspace_step(H)};
     const bool nchw_bilinear = mode == OFB_MODE_BILINEAR && !channels_last;
     const bool can_rows = nchw_bilinear && H <= 65535 * RPT_DEFAULT && (long long)H * W < (1LL << 30) && (long long)B * C * H * W < (1LL << 40);
     // TMA needs 16-byte global strides

@@ -1,8 +1,10 @@
-"""RAFT's convex flow upsampling (reference methods/raft/model/raft.py:73-85) on the K4b kernel.
+"""RAFT's convex flow upsampling (reference methods/raft/model/raft.py:73-85) on the K4b kernel and the forward
+value of `sequence_loss` (raft.py:231-260) as one fused streaming reduction.
 
-Only the hot-path static methods of the reference's `RAFT` class are provided; the network itself
+Only the hot-path static methods / functions of the reference's `raft` module are provided; the network itself
 (encoders, GRU, training loop) is out of scope and keeps running from the reference."""
-from typing import Tuple
+import ctypes
+from typing import Dict, Sequence, Tuple
 
 import torch
 from torch import Tensor
@@ -32,6 +34,49 @@ def upsample_flow(flow: Tensor, mask: Tensor) -> Tensor:
         return out
 
     return _run(run, "upsample_flow", flow, mask)
+
+
+def sequence_loss(
+    flow_preds: Sequence[Tensor],
+    flow_gt: Tensor,
+    valid: Tensor,
+    gamma: float = 0.8,
+    max_flow: float = 400.0,
+) -> Tuple[Tensor, Dict[str, float]]:
+    """Loss function defined over sequence of flow predictions (reference raft.py:231-260), forward value.
+
+    flow_preds: n tensors (B, 2, H, W); flow_gt (B, 2, H, W); valid (B, H, W).  Returns the gamma-weighted L1 loss
+    (0-dim fp32 tensor on the inputs' device) and the reference's {"1px", "3px", "5px"} metrics of the last
+    prediction.  The ground truth and validity map are read once and every prediction once; the reference makes
+    four elementwise passes per prediction.  Forward only: predictions that require grad raise on backward."""
+    n = len(flow_preds)
+    if n < 1:
+        raise ValueError("sequence_loss: need at least one flow prediction")
+    if n > ofb200.MAX_PREDICTIONS:
+        raise NotImplementedError(f"sequence_loss: at most {ofb200.MAX_PREDICTIONS} predictions, got {n}")
+    b, two, h, w = flow_gt.shape
+    if two != 2 or tuple(valid.shape) != (b, h, w) or any(tuple(p.shape) != (b, 2, h, w) for p in flow_preds):
+        raise RuntimeError(f"sequence_loss: expected predictions / flow_gt (B,2,H,W) and valid (B,H,W), got "
+                           f"{[tuple(p.shape) for p in flow_preds]}, {tuple(flow_gt.shape)}, {tuple(valid.shape)}")
+    _check_f32(flow_gt, *flow_preds)
+
+    def run(gt_d: Tensor, valid_d: Tensor, *preds_d: Tensor):
+        gt_d, valid_d = gt_d.contiguous(), valid_d.float().contiguous()
+        preds_d = [p.contiguous() for p in preds_d]
+        acc = torch.zeros(6, dtype=torch.float64, device=gt_d.device)
+        ptrs = (ctypes.c_void_p * n)(*[p.data_ptr() for p in preds_d])
+        rc = ofb200.load().ofb_sequence_loss_f32(ptrs, n, ofb200.ptr(gt_d), ofb200.ptr(valid_d), ofb200.ptr(acc),
+                                                 b, h, w, float(gamma), float(max_flow), ofb200.stream_ptr())
+        ofb200.check(rc, "ofb_sequence_loss_f32")
+        return acc
+
+    acc = _run(run, "sequence_loss", flow_gt, valid, *flow_preds)
+    host = acc.cpu()                                        # one 48-byte read-back, as the reference's .item() calls
+    loss = (acc[0] / float(b * 2 * h * w)).to(torch.float32)
+    kept = float(host[2])
+    # an empty selection is mean() of an empty tensor in the reference: NaN
+    metrics = {name: (float(host[k]) / kept if kept > 0 else float("nan")) for name, k in (("1px", 3), ("3px", 4), ("5px", 5))}
+    return loss, metrics
 
 
 class RAFT:

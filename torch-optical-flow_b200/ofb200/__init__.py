@@ -25,6 +25,7 @@ _vp = ctypes.c_void_p
 _i = ctypes.c_int
 _i64 = ctypes.c_int64
 _f = ctypes.c_float
+MAX_PREDICTIONS = 24      # OFB_MAX_PREDICTIONS (include/ofb200.h)
 
 
 class Pyramid(ctypes.Structure):
@@ -56,6 +57,7 @@ SIGNATURES = {
     "ofb_epe_reduce_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "ofb_epe_map_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "ofb_outlier_reduce_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _vp]),
+    "ofb_sequence_loss_f32": (_i, [ctypes.POINTER(_vp), _i, _vp, _vp, _vp, _i, _i, _i, ctypes.c_double, _f, _vp]),
     "ofb_pyramid_layout": (_i, [_i, _i, _i, _i, ctypes.POINTER(Pyramid), ctypes.POINTER(_i64 * MAX_LEVELS)]),
     "ofb_corr_prep_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "ofb_corr_pyramid_bf16": (_i, [_vp, _vp, _vp, ctypes.POINTER(Pyramid), _i, _i, _i, _i, _f, _i, _vp]),
