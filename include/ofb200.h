@@ -72,6 +72,16 @@ int ofb_warp_f32(const float* frame, const float* flow, float* out, uint8_t* val
                  int B, int C, int H, int W, int mode, int padding_mode, int align_corners,
                  int channels_last, int variant, float flow_mul_x, float flow_mul_y, void* stream);
 
+/* Backward of ofb_warp_f32 (bilinear, NCHW): what autograd computes for the reference's warp
+ * (operator.py:28-33: grid_sample's backward, then d grid / d flow = 1 through warp_grid :56 and the
+ * permute :28).  d_out (B,C,H,W).  d_frame_or_null (B,C,H,W) is ACCUMULATED into (zero it first):
+ * each in-bounds tap receives weight * d_out.  d_flow_or_null (B,2,H,W) is overwritten, in the
+ * units of `flow` (the flow_mul factors are applied).  Either output may be NULL. */
+int ofb_warp_backward_f32(const float* frame, const float* flow, const float* d_out,
+                          float* d_frame_or_null, float* d_flow_or_null, int B, int C, int H, int W,
+                          int padding_mode, int align_corners, float flow_mul_x, float flow_mul_y,
+                          void* stream);
+
 /* warp_grid alone (operator.py:36-56): flow (B,H,W,2) -> grid (B,H,W,2). */
 int ofb_warp_grid_f32(const float* flow_bhw2, float* grid_bhw2, int B, int H, int W, void* stream);
 

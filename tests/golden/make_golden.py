@@ -69,6 +69,23 @@ def make_warp():
     save("warp", ref_call="optical_flow.warp(frame, optical_flow.normalize(flow_px)); warp_grid", **cases)
 
 
+# ------------------------------------------------------------------ warp gradients (autograd through operator.py:8-56)
+def make_warp_grad():
+    """d(sum(weight * warp(frame, flow)))/d frame and /d flow from autograd through the UNMODIFIED reference warp."""
+    cases = {}
+    frame0 = torch.rand(2, 3, 12, 16, generator=g(90))
+    flow0 = of.normalize(5.0 * torch.randn(2, 2, 12, 16, generator=g(91)))
+    weight = torch.randn(2, 3, 12, 16, generator=g(92))
+    cases.update(frame=frame0, flow=flow0, weight=weight)
+    for pad in ("zeros", "border", "reflection"):
+        for ac in (False, True):
+            frame, flow = frame0.clone().requires_grad_(True), flow0.clone().requires_grad_(True)
+            out = of.warp(frame, flow, padding_mode=pad, align_corners=ac)
+            (out * weight).sum().backward()
+            cases[f"dframe_{pad}_{int(ac)}"], cases[f"dflow_{pad}_{int(ac)}"] = frame.grad, flow.grad
+    save("warp_grad", ref_call="autograd of (weight * optical_flow.warp(frame, flow, padding_mode, align_corners)).sum()", **cases)
+
+
 # ------------------------------------------- scale / normalize / resize / integrate / upflow8
 def make_resize():
     cases = {}
@@ -285,7 +302,11 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["sequence_loss"]:
         make_sequence_loss()
         sys.exit(0)
+    if sys.argv[1:] == ["warp_grad"]:
+        make_warp_grad()
+        sys.exit(0)
     make_warp()
+    make_warp_grad()
     make_resize()
     make_corr()
     make_upsample_epe()

@@ -122,6 +122,63 @@ def test_warp_vs_oracle(shape, sigma, pad, ac):
     assert maxabs(N(normalize(T(flow_px))), flow) == 0.0
 
 
+@pytest.mark.parametrize("pad", ["zeros", "border", "reflection"])
+@pytest.mark.parametrize("ac", [False, True])
+def test_warp_backward_golden(golden, pad, ac):
+    """Backward kernel against the gradients autograd produced through the unmodified reference warp."""
+    from optical_flow import warp
+
+    g = golden("warp_grad")
+    frame, flow = T(g["frame"]).requires_grad_(True), T(g["flow"]).requires_grad_(True)
+    out = warp(frame, flow, padding_mode=pad, align_corners=ac)
+    (out * T(g["weight"])).sum().backward()
+    want_f, want_w = g[f"dframe_{pad}_{int(ac)}"], g[f"dflow_{pad}_{int(ac)}"]
+    assert maxabs(N(frame.grad), want_f) <= 1e-5 * max(1.0, np.abs(want_f).max())
+    assert maxabs(N(flow.grad), want_w) <= 1e-5 * max(1.0, np.abs(want_w).max())
+
+
+@pytest.mark.parametrize("shape,sigma", [((2, 3, 70, 130), 5.0), ((1, 2, 368, 496), 30.0), ((3, 5, 33, 257), 2.0)])
+@pytest.mark.parametrize("pad,ac", [("border", False), ("zeros", False), ("reflection", True), ("border", True)])
+def test_warp_backward_vs_oracle(shape, sigma, pad, ac):
+    """Backward kernel against autograd through oracle/torch_port.py (pinned to the reference's gradients on CPU):
+    both gradients, each alone, the fused pixel-flow variant, host tensors and the forward-with-mask form."""
+    from oracle import torch_port as tp
+    from optical_flow import warp
+
+    r = rng(31)
+    b, c, h, w = shape
+    frame = r.random(shape, dtype=np.float32)
+    flow_px = (sigma * r.standard_normal((b, 2, h, w))).astype(np.float32)
+    flow = oracle.normalize(flow_px).astype(np.float32)
+    weight = r.standard_normal(shape).astype(np.float32)
+    cf, cw = torch.from_numpy(frame).requires_grad_(True), torch.from_numpy(flow).requires_grad_(True)
+    (tp.warp(cf, cw, padding_mode=pad, align_corners=ac) * torch.from_numpy(weight)).sum().backward()
+    want_f, want_w = cf.grad.numpy(), cw.grad.numpy()
+    tol_f, tol_w = 1e-5 * max(1.0, np.abs(want_f).max()), 2e-5 * max(1.0, np.abs(want_w).max())
+
+    gf, gw = T(frame).requires_grad_(True), T(flow).requires_grad_(True)
+    out, mask = warp(gf, gw, padding_mode=pad, align_corners=ac, return_mask=True)
+    assert not mask.requires_grad
+    (out * T(weight)).sum().backward()
+    assert maxabs(N(gf.grad), want_f) <= tol_f and maxabs(N(gw.grad), want_w) <= tol_w
+    # one gradient at a time
+    only_f = T(frame).requires_grad_(True)
+    (warp(only_f, T(flow), padding_mode=pad, align_corners=ac) * T(weight)).sum().backward()
+    assert maxabs(N(only_f.grad), want_f) <= tol_f
+    only_w = T(flow).requires_grad_(True)
+    (warp(T(frame), only_w, padding_mode=pad, align_corners=ac) * T(weight)).sum().backward()
+    assert torch.equal(only_w.grad, gw.grad)
+    # pixel-unit flow with the fused normalize: chain rule through the 2/(W-1), 2/(H-1) factors
+    px = T(flow_px).requires_grad_(True)
+    (warp(T(frame), px, padding_mode=pad, align_corners=ac, pixel_flow=True) * T(weight)).sum().backward()
+    fac = np.array([2.0 / max(w - 1, 1), 2.0 / max(h - 1, 1)], np.float32).reshape(1, 2, 1, 1)
+    assert maxabs(N(px.grad), want_w * fac) <= tol_w * float(fac.max())
+    # host tensors: staged through the GPU, gradients come back on the host
+    hf = torch.from_numpy(frame).requires_grad_(True)
+    (warp(hf, torch.from_numpy(flow), padding_mode=pad, align_corners=ac) * torch.from_numpy(weight)).sum().backward()
+    assert not hf.grad.is_cuda and maxabs(hf.grad.numpy(), want_f) <= tol_f
+
+
 def test_warp_channels_last_and_host_tensors():
     from optical_flow import warp
 
@@ -165,7 +222,7 @@ def test_warp_full_size_properties():
 
 
 def test_warp_errors():
-    from optical_flow import scale, warp
+    from optical_flow import resize, scale, warp
 
     x = torch.zeros(1, 3, 4, 4, device="cuda")
     f = torch.zeros(1, 2, 4, 4, device="cuda")
@@ -179,8 +236,10 @@ def test_warp_errors():
         scale(torch.zeros(1, 3, 4, 4, device="cuda"), 2.0)
     with pytest.raises(AssertionError):
         scale(f, (1.0, 2.0, 3.0))
-    with pytest.raises(NotImplementedError):
-        warp(x.requires_grad_(), f).sum().backward()
+    with pytest.raises(NotImplementedError):                      # nearest has no backward kernel
+        warp(x.requires_grad_(), f, mode="nearest").sum().backward()
+    with pytest.raises(NotImplementedError):                      # forward-only ops say so instead of returning zeros
+        resize(f.clone().requires_grad_(), scale_factor=2.0).sum().backward()
 
 
 def test_warp_grid_and_integrate_golden(golden):

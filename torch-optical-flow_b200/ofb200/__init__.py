@@ -50,6 +50,7 @@ SIGNATURES = {
     "ofb_strerror": (ctypes.c_char_p, [_i]),
     "ofb_launch_count": (_i64, []),
     "ofb_warp_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp]),
+    "ofb_warp_backward_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _f, _vp]),
     "ofb_warp_grid_f32": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "ofb_scale_flow_f32": (_i, [_vp, _vp, _i, _i64, _f, _f, _vp]),
     "ofb_resize_bilinear_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp]),
@@ -147,6 +148,32 @@ class _NoBackward(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grads):
         raise NotImplementedError(f"{ctx.op_name}: backward is not implemented (forward-only B200 kernels)")
+
+
+class _WithBackward(torch.autograd.Function):
+    """A forward kernel with a hand-written backward kernel: `bwd(saved_inputs, grad_out, needs_input_grad)`
+    returns one gradient (or None) per input tensor.  Extra outputs (masks, indices) are non-differentiable."""
+
+    @staticmethod
+    def forward(ctx, fn, bwd, name, *tensors):
+        ctx.bwd, ctx.op_name = bwd, name
+        det = [t.detach() for t in tensors]
+        out = fn(*det)
+        ctx.save_for_backward(*det)
+        if isinstance(out, tuple):
+            ctx.mark_non_differentiable(*out[1:])
+        return out
+
+    @staticmethod
+    def backward(ctx, *grads):
+        res = ctx.bwd(ctx.saved_tensors, grads[0], ctx.needs_input_grad[3:])
+        return (None, None, None) + tuple(res)
+
+
+def differentiable(fn, bwd, name, *tensors):
+    if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
+        return _WithBackward.apply(fn, bwd, name, *tensors)
+    return fn(*tensors)
 
 
 def forward_only(fn, name, *tensors):

@@ -18,12 +18,13 @@ def _check_f32(*tensors: Tensor) -> None:
             raise NotImplementedError(f"ofb200 kernels are fp32 only, got {t.dtype}")
 
 
-def _run(fn, name: str, *tensors: Tensor) -> Tensor:
-    """Stage inputs on the device, run the forward-only kernel, return on the inputs' device."""
+def _run(fn, name: str, *tensors: Tensor, bwd=None) -> Tensor:
+    """Stage inputs on the device, run the kernel (forward-only unless a backward kernel is given), return on
+    the inputs' device."""
     on_host = not tensors[0].is_cuda
     dev = [ofb200.to_device(t) for t in tensors]
     with torch.cuda.device(dev[0].device):
-        out = ofb200.forward_only(fn, name, *dev)
+        out = ofb200.differentiable(fn, bwd, name, *dev) if bwd else ofb200.forward_only(fn, name, *dev)
     if on_host:
         out = tuple(o.cpu() for o in out) if isinstance(out, tuple) else out.cpu()
     return out
@@ -89,7 +90,25 @@ def warp(
         ofb200.check(rc, "ofb_warp_f32")
         return (out, mask.bool()) if return_mask else out
 
-    return _run(run, "warp", frame, flow)
+    def backward(saved, grad_out: Tensor, needs):
+        """d warp / d frame (scatter-add of the bilinear weights) and d warp / d flow, as F.grid_sample's backward
+        through warp_grid (reference operator.py:28-33,56)."""
+        if mode != "bilinear":
+            raise NotImplementedError("warp: backward exists for mode='bilinear' only")
+        frame_d, flow_d = saved
+        with torch.cuda.device(frame_d.device):
+            frame_c, flow_c = frame_d.contiguous(), flow_d.contiguous()
+            grad_c = grad_out.contiguous()
+            d_frame = torch.zeros((b, c, h, w), dtype=torch.float32, device=frame_c.device) if needs[0] else None
+            d_flow = torch.empty((b, 2, h, w), dtype=torch.float32, device=frame_c.device) if needs[1] else None
+            rc = ofb200.load().ofb_warp_backward_f32(
+                ofb200.ptr(frame_c), ofb200.ptr(flow_c), ofb200.ptr(grad_c), ofb200.ptr(d_frame), ofb200.ptr(d_flow),
+                b, c, h, w, ofb200.PAD[padding_mode], int(bool(align_corners)), mul_x, mul_y, ofb200.stream_ptr(),
+            )
+            ofb200.check(rc, "ofb_warp_backward_f32")
+        return d_frame, d_flow
+
+    return _run(run, "warp", frame, flow, bwd=backward)
 
 
 def warp_grid(flow: Tensor) -> Tensor:
