@@ -106,6 +106,12 @@ int ofb_resize_bilinear_f32(const float* in, float* out, int N, int C, int H, in
  * (methods/raft/model/raft.py:73-85): flow (N,2,h,w), mask (N,576,h,w) -> out (N,2,8h,8w).
  * ------------------------------------------------------------------------------------- */
 int ofb_convex_upsample_f32(const float* flow, const float* mask, float* out, int N, int h, int w, void* stream);
+/* Backward of the convex upsampling (autograd through raft.py:77-85): d_out (N,2,8h,8w), 16-byte
+ * aligned.  d_mask_or_null (N,576,h,w) is overwritten; d_flow_or_null (N,2,h,w) is ACCUMULATED
+ * into (zero it first).  Either may be NULL. */
+int ofb_convex_upsample_backward_f32(const float* flow, const float* mask, const float* d_out,
+                                     float* d_flow_or_null, float* d_mask_or_null, int N, int h, int w,
+                                     void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * K4c  end-point-error reduction.  Replaces AverageEndPointError.update
@@ -136,6 +142,11 @@ int ofb_outlier_reduce_f32(const float* pred, const float* target, const float* 
 int ofb_sequence_loss_f32(const float* const* preds, int n_predictions, const float* flow_gt,
                           const float* valid, double* acc, int B, int H, int W, double gamma,
                           float max_flow, void* stream);
+/* Its backward: d_preds[i] (HOST array of device pointers, NULL entries skipped) is overwritten with
+ * grad_loss[0] * gamma^(n-1-i) / (B*2*H*W) * keep * sign(preds[i] - flow_gt); grad_loss is a DEVICE scalar. */
+int ofb_sequence_loss_backward_f32(const float* const* preds, float* const* d_preds, int n_predictions,
+                                   const float* flow_gt, const float* valid, const float* grad_loss,
+                                   int B, int H, int W, double gamma, float max_flow, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Correlation pyramid layout (owned by the caller, described by ofb_pyramid_layout).

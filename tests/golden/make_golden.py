@@ -250,6 +250,29 @@ def make_sequence_loss():
     save("sequence_loss", ref_call="model.raft.sequence_loss(flow_preds, flow_gt, valid, gamma, max_flow)", **cases)
 
 
+# ------------------------------------------------------ gradients of upsample_flow / sequence_loss (autograd)
+def make_raft_grad():
+    """Gradients autograd produces through the UNMODIFIED RAFT.upsample_flow and sequence_loss."""
+    from model.raft import sequence_loss
+
+    cases = {}
+    flow = (2.0 * torch.randn(2, 2, 5, 7, generator=g(100))).requires_grad_(True)
+    mask = (3.0 * torch.randn(2, 576, 5, 7, generator=g(101))).requires_grad_(True)
+    weight = torch.randn(2, 2, 40, 56, generator=g(102))
+    (RAFT.upsample_flow(flow, mask) * weight).sum().backward()
+    cases.update(up_flow=flow.detach(), up_mask=mask.detach(), up_weight=weight, up_dflow=flow.grad, up_dmask=mask.grad)
+    gt = 6.0 * torch.randn(2, 2, 12, 20, generator=g(103))
+    gt[1, :, 2, 3] = 900.0
+    valid = (torch.rand(2, 12, 20, generator=g(104)) > 0.25).float()
+    preds = [(gt + (2.0 / (i + 1)) * torch.randn(2, 2, 12, 20, generator=g(105 + i))).requires_grad_(True) for i in range(4)]
+    preds[1].data[0, 0, 0, 0] = gt[0, 0, 0, 0]               # an exact zero difference: sign(0) = 0
+    loss, _ = sequence_loss(preds, gt, valid, gamma=0.8)
+    (3.0 * loss).backward()
+    cases.update(sl_gt=gt, sl_valid=valid, sl_preds=torch.stack([p.detach() for p in preds]),
+                 sl_dpreds=torch.stack([p.grad for p in preds]))
+    save("raft_grad", ref_call="autograd through RAFT.upsample_flow and model.raft.sequence_loss", **cases)
+
+
 # ------------------------------------------------------ RAFT.forward trace (raft.py:87-147)
 def make_raft_trace():
     """Run the UNMODIFIED reference RAFT (random weights, eval mode) on one small image pair and record
@@ -305,10 +328,14 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["warp_grad"]:
         make_warp_grad()
         sys.exit(0)
+    if sys.argv[1:] == ["raft_grad"]:
+        make_raft_grad()
+        sys.exit(0)
     make_warp()
     make_warp_grad()
     make_resize()
     make_corr()
     make_upsample_epe()
     make_sequence_loss()
+    make_raft_grad()
     make_raft_trace()

@@ -389,6 +389,52 @@ def test_outlier_ratio_golden_and_oracle(golden):
     assert float(m._acc[0]) == s and int(m.total) == n
 
 
+def test_upsample_and_sequence_loss_backward(golden):
+    """Backward kernels of the convex upsampling and of sequence_loss: the reference's own autograd gradients
+    (tests/golden/raft_grad.npz), then larger cases against autograd through oracle/torch_port.py."""
+    from model import sequence_loss, upsample_flow
+    from oracle import torch_port as tp
+
+    g = golden("raft_grad")
+    flow, mask = T(g["up_flow"]).requires_grad_(True), T(g["up_mask"]).requires_grad_(True)
+    (upsample_flow(flow, mask) * T(g["up_weight"])).sum().backward()
+    assert maxabs(N(flow.grad), g["up_dflow"]) <= 1e-5 * np.abs(g["up_dflow"]).max()
+    assert maxabs(N(mask.grad), g["up_dmask"]) <= 1e-5 * max(1.0, np.abs(g["up_dmask"]).max())
+    preds = [T(g["sl_preds"][i]).requires_grad_(True) for i in range(g["sl_preds"].shape[0])]
+    loss, _ = sequence_loss(preds, T(g["sl_gt"]), T(g["sl_valid"]), gamma=0.8)
+    (3.0 * loss).backward()
+    for i, p in enumerate(preds):
+        assert maxabs(N(p.grad), g["sl_dpreds"][i]) <= 1e-6 * np.abs(g["sl_dpreds"]).max(), i
+
+    r = rng(41)
+    for (n, h, w) in [(2, 47, 156), (1, 3, 5), (3, 17, 33)]:
+        fl = r.standard_normal((n, 2, h, w)).astype(np.float32)
+        mk = (2 * r.standard_normal((n, 576, h, w))).astype(np.float32)
+        wt = r.standard_normal((n, 2, 8 * h, 8 * w)).astype(np.float32)
+        cf, cm = torch.from_numpy(fl).requires_grad_(True), torch.from_numpy(mk).requires_grad_(True)
+        (tp.upsample_flow(cf, cm) * torch.from_numpy(wt)).sum().backward()
+        gf, gm = T(fl).requires_grad_(True), T(mk).requires_grad_(True)
+        (upsample_flow(gf, gm) * T(wt)).sum().backward()
+        assert maxabs(N(gf.grad), cf.grad.numpy()) <= 2e-5 * np.abs(cf.grad.numpy()).max(), (n, h, w)
+        assert maxabs(N(gm.grad), cm.grad.numpy()) <= 2e-5 * max(1.0, np.abs(cm.grad.numpy()).max()), (n, h, w)
+        only = T(mk).requires_grad_(True)                       # mask gradient alone
+        (upsample_flow(T(fl), only) * T(wt)).sum().backward()
+        assert torch.equal(only.grad, gm.grad)
+    for (b, h, w, n) in [(2, 376, 1248, 12), (3, 11, 17, 3)]:
+        gt = (8 * r.standard_normal((b, 2, h, w))).astype(np.float32)
+        valid = (r.random((b, h, w)) > 0.3).astype(np.float32)
+        ps = [(gt + (4.0 / (i + 1)) * r.standard_normal(gt.shape)).astype(np.float32) for i in range(n)]
+        cp = [torch.from_numpy(p).requires_grad_(True) for p in ps]
+        tp.sequence_loss(cp, torch.from_numpy(gt), torch.from_numpy(valid), gamma=0.85)[0].backward()
+        gp = [T(p).requires_grad_(i != 1) for i, p in enumerate(ps)]   # one prediction without grad
+        sequence_loss(gp, T(gt), T(valid), gamma=0.85)[0].backward()
+        for i in range(n):
+            if i == 1:
+                assert gp[i].grad is None
+            else:
+                assert maxabs(N(gp[i].grad), cp[i].grad.numpy()) <= 1e-6 * np.abs(cp[i].grad.numpy()).max(), (b, h, w, i)
+
+
 def test_sequence_loss_golden_and_oracle(golden):
     """sequence_loss (reference methods/raft/model/raft.py:231-260) as one fused reduction: the reference's own
     outputs, then a 12-prediction KITTI-size case against the oracle (counts exact, loss to 1e-6 relative), a

@@ -89,6 +89,31 @@ def bench_warp_c2(variants=(0,), flows=("white5px", "smooth5px"), masks=(1,)):
     return recs
 
 
+def bench_warp_bwd_c2(flows=("white5px", "smooth5px")):
+    """C2 backward: d frame (scatter-add) + d flow, 32x3x436x1024 fp32.  Bytes: frame, flow, d_out read; d_flow written;
+    d_frame read-modify-written = 4 * (C + 2 + C + 2 + 2C) per pixel."""
+    b, c, h, w = 32, 3, 436, 1024
+    gen = torch.Generator(device="cuda").manual_seed(1234)
+    frame = torch.rand((b, c, h, w), device="cuda", generator=gen)
+    d_out = torch.randn((b, c, h, w), device="cuda", generator=gen)
+    mk = {"white5px": lambda: normalize(5 * torch.randn((b, 2, h, w), device="cuda", generator=gen)),
+          "smooth5px": lambda: normalize(smooth_flow(b, h, w, 5.0, gen))}
+    lib = ofb200.load()
+    d_frame = torch.zeros_like(frame)
+    d_flow = torch.empty((b, 2, h, w), device="cuda")
+    recs = []
+    for fname in flows:
+        flow = mk[fname]()
+
+        def run():
+            rc = lib.ofb_warp_backward_f32(ofb200.ptr(frame), ofb200.ptr(flow), ofb200.ptr(d_out), ofb200.ptr(d_frame),
+                                           ofb200.ptr(d_flow), b, c, h, w, 1, 0, 1.0, 1.0, ofb200.stream_ptr())
+            assert rc == 0
+        ms = timeit(run)
+        recs.append(record(f"C2 K1 warp backward 32x3x436x1024 flow={fname}", ms, nbytes=b * h * w * 4 * (4 * c + 4)))
+    return recs
+
+
 def _corr_setup(b, c, h, w, seed=1):
     gen = torch.Generator(device="cuda").manual_seed(seed)
     f1 = torch.randn((b, c, h, w), device="cuda", generator=gen)

@@ -175,6 +175,41 @@ __global__ void __launch_bounds__(NT) sequence_loss_kernel(const __grid_constant
     }
 }
 
+// Backward of sequence_loss: d loss / d pred_i = grad * gamma^(n-1-i) / (B*2*H*W) * keep * sign(pred_i - gt)
+// (autograd of raft.py:247-250: abs -> sign, mean -> 1/numel, the mask multiplies).  One elementwise pass that
+// reads the ground truth / validity once and writes all n gradients.
+struct GradList {
+    float* p[MAX_PREDS];
+};
+
+__global__ void __launch_bounds__(NT) sequence_loss_bwd_kernel(const __grid_constant__ PredList preds,
+                                                               const __grid_constant__ GradList grads, int n,
+                                                               const float* __restrict__ gt, const float* __restrict__ valid,
+                                                               const float* __restrict__ grad_loss, int B, int64_t HW,
+                                                               float max_flow, double inv_numel) {
+    const double g0 = (double)__ldg(grad_loss) * inv_numel;
+    const int64_t total = (int64_t)B * HW;
+    for (int64_t t = (int64_t)blockIdx.x * NT + threadIdx.x; t < total; t += (int64_t)gridDim.x * NT) {
+        const int64_t b = t / HW, q = t - b * HW;
+        const int64_t ox = (b * 2 + 0) * HW + q, oy = (b * 2 + 1) * HW + q;
+        const float gx = __ldg(gt + ox), gy = __ldg(gt + oy);
+        const float mag = sqrtf(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)));
+        const bool keep = __ldg(valid + t) >= 0.5f && mag < max_flow;
+        for (int i = 0; i < n; ++i) {
+            if (!grads.p[i]) continue;
+            float dx = 0.0f, dy = 0.0f;
+            if (keep) {
+                const float w = (float)(g0 * preds.w[i]);
+                const float ex = __ldg(preds.p[i] + ox) - gx, ey = __ldg(preds.p[i] + oy) - gy;
+                dx = ex > 0.0f ? w : (ex < 0.0f ? -w : 0.0f);
+                dy = ey > 0.0f ? w : (ey < 0.0f ? -w : 0.0f);
+            }
+            grads.p[i][ox] = dx;
+            grads.p[i][oy] = dy;
+        }
+    }
+}
+
 }  // namespace
 
 namespace {
@@ -244,6 +279,34 @@ OFB_API int ofb_sequence_loss_f32(const float* const* preds, int n_predictions, 
     if (blocks > cap) blocks = cap;
     sequence_loss_kernel<<<(int)blocks, NT, 0, (cudaStream_t)stream>>>(pl, n_predictions, flow_gt, valid, acc, B, HW, vec,
                                                                       max_flow);
+    OFB_LAUNCH_CHECK();
+    return OFB_OK;
+}
+
+OFB_API int ofb_sequence_loss_backward_f32(const float* const* preds, float* const* d_preds, int n_predictions,
+                                           const float* flow_gt, const float* valid, const float* grad_loss, int B, int H,
+                                           int W, double gamma, float max_flow, void* stream) {
+    if (!preds || !d_preds || !flow_gt || !valid || !grad_loss || B < 0 || H < 0 || W < 0 || n_predictions < 1)
+        return OFB_EINVAL;
+    if (n_predictions > MAX_PREDS) return OFB_EUNSUPPORTED;
+    const int64_t HW = (int64_t)H * W;
+    if ((int64_t)B * HW == 0) return OFB_OK;
+    PredList pl;
+    GradList gl;
+    for (int i = 0; i < MAX_PREDS; ++i) { pl.p[i] = nullptr; pl.w[i] = 0.0; gl.p[i] = nullptr; }
+    double wgt = 1.0;
+    for (int i = n_predictions - 1; i >= 0; --i) {
+        if (!preds[i]) return OFB_EINVAL;
+        pl.p[i] = preds[i];
+        pl.w[i] = wgt;
+        gl.p[i] = d_preds[i];
+        wgt *= gamma;
+    }
+    int64_t blocks = ((int64_t)B * HW + NT - 1) / NT;
+    const int cap = ofb_num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    sequence_loss_bwd_kernel<<<(int)blocks, NT, 0, (cudaStream_t)stream>>>(
+        pl, gl, n_predictions, flow_gt, valid, grad_loss, B, HW, max_flow, 1.0 / ((double)B * 2.0 * (double)HW));
     OFB_LAUNCH_CHECK();
     return OFB_OK;
 }
