@@ -238,6 +238,13 @@ int ofb_corr_lookup(const ofb_pyramid* pyr_host, const float* coords, float* out
                     int32_t* idx_or_null, uint8_t* valid_or_null, int B, int h, int w, int radius,
                     void* stream);
 
+/* Backward of ofb_corr_lookup with respect to the pyramid (autograd through corr.py:56-77 /
+ * utils.py:64-80; the coordinates get no gradient -- RAFT detaches them, raft.py:127).
+ * d_pyr: fp32, OFB_LAYOUT_ROWS (ofb_pyramid_layout mode 0 or 1), ACCUMULATED into -- zero it before the
+ * first of the refinement iterations, then call once per lookup.  d_out (B, L*(2r+1)^2, h, w). */
+int ofb_corr_lookup_backward_f32(const ofb_pyramid* d_pyr, const float* coords, const float* d_out,
+                                 int B, int h, int w, int radius, void* stream);
+
 /* bilinear_sampler (utils.py:64-80) for arbitrary images: img (N,C,H,W), coords (N,Ho,Wo,2)
  * pixel units -> out (N,C,Ho,Wo) [+ mask (N,Ho,Wo) fp32 0/1]. */
 int ofb_bilinear_sampler_f32(const float* img, const float* coords, float* out, float* mask_or_null,

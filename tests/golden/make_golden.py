@@ -273,6 +273,30 @@ def make_raft_grad():
     save("raft_grad", ref_call="autograd through RAFT.upsample_flow and model.raft.sequence_loss", **cases)
 
 
+# ------------------------------------------------------ gradients of the correlation block (autograd)
+def make_corr_grad():
+    """d(sum_k weight_k * CorrBlock(fmap1, fmap2)(coords_k))/d fmap1, /d fmap2 through the UNMODIFIED reference
+    (matmul, avg_pool2d chain, grid_sample), two lookups accumulating into the same pyramid."""
+    cases = {}
+    b, c, h, w = 1, 64, 16, 20
+    f1 = torch.randn(b, c, h, w, generator=g(120)).requires_grad_(True)
+    f2 = torch.randn(b, c, h, w, generator=g(121)).requires_grad_(True)
+    base = utils.coords_grid(b, h, w)
+    blk = corr_mod.CorrBlock(f1, f2, num_levels=4, radius=4)
+    total = 0.0
+    for k in range(2):
+        coords = base + 3.0 * torch.randn(b, 2, h, w, generator=g(122 + k))
+        if k == 0:
+            coords[0, :, 0, :4] = base[0, :, 0, :4]           # integer coordinates (RAFT's first iteration)
+            coords[0, 0, 3, 3] = -40.0                        # a window entirely outside
+        weight = torch.randn(b, 4 * 81, h, w, generator=g(130 + k))
+        total = total + (blk(coords) * weight).sum()
+        cases[f"coords{k}"], cases[f"weight{k}"] = coords, weight
+    total.backward()
+    cases.update(fmap1=f1.detach(), fmap2=f2.detach(), dfmap1=f1.grad, dfmap2=f2.grad)
+    save("corr_grad", ref_call="autograd through CorrBlock(fmap1, fmap2, 4, 4)(coords) x2", **cases)
+
+
 # ------------------------------------------------------ RAFT.forward trace (raft.py:87-147)
 def make_raft_trace():
     """Run the UNMODIFIED reference RAFT (random weights, eval mode) on one small image pair and record
@@ -331,6 +355,9 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["raft_grad"]:
         make_raft_grad()
         sys.exit(0)
+    if sys.argv[1:] == ["corr_grad"]:
+        make_corr_grad()
+        sys.exit(0)
     make_warp()
     make_warp_grad()
     make_resize()
@@ -338,4 +365,5 @@ if __name__ == "__main__":
     make_upsample_epe()
     make_sequence_loss()
     make_raft_grad()
+    make_corr_grad()
     make_raft_trace()

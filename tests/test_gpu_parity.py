@@ -389,6 +389,48 @@ def test_outlier_ratio_golden_and_oracle(golden):
     assert float(m._acc[0]) == s and int(m.total) == n
 
 
+def test_corr_block_backward(golden):
+    """CorrBlock gradients with respect to the feature maps: the reference's autograd result (two lookups into one
+    pyramid, tests/golden/corr_grad.npz), then other shapes / radii / level counts against autograd through
+    oracle/torch_port.py.  The gradients do not depend on the stored (bf16) volume, only on the fp32 feature maps
+    and the lookup weights, so the tolerance is fp32 summation noise."""
+    from model import CorrBlock
+    from oracle import torch_port as tp
+
+    g = golden("corr_grad")
+    f1, f2 = T(g["fmap1"]).requires_grad_(True), T(g["fmap2"]).requires_grad_(True)
+    blk = CorrBlock(f1, f2, num_levels=4, radius=4)
+    total = sum((blk(T(g[f"coords{k}"])) * T(g[f"weight{k}"])).sum() for k in range(2))
+    total.backward()
+    for got, want in ((N(f1.grad), g["dfmap1"]), (N(f2.grad), g["dfmap2"])):
+        assert maxabs(got, want) <= 2e-5 * np.abs(want).max()
+    assert blk._dpyr is None                                       # the gradient pyramid is freed once consumed
+
+    r = rng(51)
+    for (b, c, h, w, lv, rad, dt) in [(1, 64, 9, 13, 2, 3, torch.bfloat16), (2, 32, 8, 20, 3, 2, torch.float32),
+                                      (1, 128, 24, 40, 4, 4, torch.bfloat16)]:
+        a1 = r.standard_normal((b, c, h, w)).astype(np.float32)
+        a2 = r.standard_normal((b, c, h, w)).astype(np.float32)
+        base = np.stack(np.meshgrid(np.arange(w), np.arange(h)), 0)[None].astype(np.float32)
+        cs = [(base + 2.5 * r.standard_normal((b, 2, h, w))).astype(np.float32) for _ in range(3)]
+        ws = [r.standard_normal((b, lv * (2 * rad + 1) ** 2, h, w)).astype(np.float32) for _ in range(3)]
+        c1, c2 = torch.from_numpy(a1).requires_grad_(True), torch.from_numpy(a2).requires_grad_(True)
+        pyr = tp.corr_pyramid(c1, c2, lv)
+        sum((tp.corr_lookup(pyr, torch.from_numpy(x), rad) * torch.from_numpy(y)).sum() for x, y in zip(cs, ws)).backward()
+        g1, g2 = T(a1).requires_grad_(True), T(a2).requires_grad_(True)
+        blk = CorrBlock(g1, g2, num_levels=lv, radius=rad, pyramid_dtype=dt)
+        sum((blk(T(x)) * T(y)).sum() for x, y in zip(cs, ws)).backward()
+        assert maxabs(N(g1.grad), c1.grad.numpy()) <= 5e-5 * np.abs(c1.grad.numpy()).max(), (b, c, h, w, lv, rad)
+        assert maxabs(N(g2.grad), c2.grad.numpy()) <= 5e-5 * np.abs(c2.grad.numpy()).max(), (b, c, h, w, lv, rad)
+    # only fmap2 requires grad; no_grad lookups stay forward-only
+    g2 = T(a2).requires_grad_(True)
+    blk = CorrBlock(T(a1), g2, num_levels=lv, radius=rad)
+    with torch.no_grad():
+        assert not blk(T(cs[0])).requires_grad
+    (blk(T(cs[0])) * T(ws[0])).sum().backward()
+    assert g2.grad is not None and bool(torch.isfinite(g2.grad).all())
+
+
 def test_upsample_and_sequence_loss_backward(golden):
     """Backward kernels of the convex upsampling and of sequence_loss: the reference's own autograd gradients
     (tests/golden/raft_grad.npz), then larger cases against autograd through oracle/torch_port.py."""

@@ -6,7 +6,8 @@ Differences a caller can observe, all deliberate:
     padded buffer (row pitch rounded up to 8 elements for TMA) and is stored in bf16 by default
     (the reference's shipped configs run `precision: 16`, so its stored volume is half precision
     too); pass `pyramid_dtype=torch.float32` for an fp32 pyramid (CUDA-core builder).
-  * forward only.
+  * differentiable with respect to the feature maps (K3 backward kernel + two library GEMMs per level); the
+    lookup coordinates get no gradient (the reference's RAFT detaches them, raft.py:127).
 """
 import ctypes
 import math
@@ -58,6 +59,74 @@ def prepare_operands(fmap1: Tensor, fmap2: Tensor, num_levels: int):
     return a_km, b_km, q_km
 
 
+class _PyramidHandle(torch.autograd.Function):
+    """Graph node standing for "the pyramid built from (fmap1, fmap2)".  Its output is a dummy scalar every
+    lookup depends on; autograd therefore runs this backward after all the lookups' backwards, when the gradient
+    pyramid is complete, and turns it into feature-map gradients:
+        pyr_l = fmap1^T . pool_l(fmap2) / sqrt(C)        (pooling is linear, reference corr.py:45-54)
+        d fmap1 = sum_l pool_l(fmap2) . dP_l^T / sqrt(C);  d pool_l(fmap2) = fmap1 . dP_l / sqrt(C)
+    (library GEMMs over the dense fp32 gradient levels), and the pooling adjoint through autograd."""
+
+    @staticmethod
+    def forward(ctx, block, fmap1, fmap2):
+        ctx.block = block
+        ctx.save_for_backward(fmap1.detach(), fmap2.detach())
+        return torch.zeros(1, dtype=torch.float32, device=fmap1.device)
+
+    @staticmethod
+    def backward(ctx, _grad_handle):
+        blk = ctx.block
+        fmap1, fmap2 = ctx.saved_tensors
+        b, c, h, w = fmap1.shape
+        d1 = d2 = None
+        if blk._dpyr is not None:
+            scale = 1.0 / math.sqrt(float(c))
+            f1 = fmap1.float().reshape(b, c, h * w)
+            with torch.enable_grad():
+                leaf = fmap2.float().detach().requires_grad_(True)
+                levels, cur = [leaf], leaf
+                for _ in range(blk.num_levels - 1):
+                    cur = torch.nn.functional.avg_pool2d(cur, 2, stride=2)
+                    levels.append(cur)
+            d1 = torch.zeros_like(f1)
+            d_levels = []
+            for lvl, f2l in enumerate(levels):
+                hl, wl = f2l.shape[-2:]
+                dp = blk._dpyr[lvl].view(b, h * w, hl * wl)                          # (B, N, N_l), tight rows
+                d1.baddbmm_(f2l.detach().reshape(b, c, hl * wl), dp.transpose(1, 2), alpha=scale)
+                d_levels.append((torch.bmm(f1, dp) * scale).view(b, c, hl, wl))
+            d2 = torch.autograd.grad(levels, leaf, d_levels)[0]
+            d1 = d1.view(b, c, h, w).to(fmap1.dtype)
+            d2 = d2.to(fmap2.dtype)
+            blk._dpyr = None                                                         # free the gradient pyramid
+        need1, need2 = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        return None, (d1 if need1 else None), (d2 if need2 else None)
+
+
+class _LookupFn(torch.autograd.Function):
+    """One CorrBlock.__call__: forward = the K3 kernel, backward = scatter into the block's gradient pyramid."""
+
+    @staticmethod
+    def forward(ctx, block, coords_d, handle):
+        ctx.block = block
+        ctx.save_for_backward(coords_d)
+        return block._lookup(coords_d, None, None, None)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        blk = ctx.block
+        (coords_d,) = ctx.saved_tensors
+        b, c, h, w = blk._shape
+        with torch.cuda.device(blk._dev):
+            if blk._dpyr is None:
+                blk._alloc_grad_pyramid()
+            rc = ofb200.load().ofb_corr_lookup_backward_f32(
+                ctypes.byref(blk._dpyr_desc), ofb200.ptr(coords_d), ofb200.ptr(grad_out.contiguous()), b, h, w, blk.radius,
+                ofb200.stream_ptr())
+            ofb200.check(rc, "ofb_corr_lookup_backward_f32")
+        return None, None, torch.zeros(1, dtype=torch.float32, device=blk._dev)
+
+
 class CorrBlock:
     def __init__(
         self,
@@ -81,6 +150,11 @@ class CorrBlock:
         if pyramid_dtype not in (torch.float32, torch.bfloat16):
             raise NotImplementedError("CorrBlock: pyramid_dtype must be torch.float32 or torch.bfloat16")
         self._on_host = not fmap1.is_cuda
+        # training: keep the differentiable feature maps behind a handle node the lookups depend on
+        self._handle = None
+        self._dpyr = None
+        if torch.is_grad_enabled() and (fmap1.requires_grad or fmap2.requires_grad):
+            self._handle = _PyramidHandle.apply(self, ofb200.to_device(fmap1), ofb200.to_device(fmap2))
         fmap1 = ofb200.to_device(fmap1).detach()
         fmap2 = ofb200.to_device(fmap2).detach()
         if fmap1.dtype != torch.float32:
@@ -182,25 +256,56 @@ class CorrBlock:
         coords_d = ofb200.to_device(coords).detach().contiguous()
         d = 2 * self.radius + 1
         lvls = self.num_levels
-        with torch.cuda.device(self._dev):
-            oshape = (b, lvls * d * d, h, w)
-            if out is None:
-                out = torch.empty(oshape, dtype=torch.float32, device=self._dev)
-            elif (tuple(out.shape) != oshape or out.dtype != torch.float32 or not out.is_cuda
-                  or not out.is_contiguous()):
-                raise RuntimeError(f"CorrBlock: out must be a contiguous fp32 CUDA tensor of shape {oshape}")
-            idx = torch.empty((b * h * w, lvls, 2, d), dtype=torch.int32, device=self._dev) if return_index else None
-            valid = torch.empty((b * h * w, lvls, d * d), dtype=torch.uint8, device=self._dev) if return_index else None
-            rc = ofb200.load().ofb_corr_lookup(
-                ctypes.byref(self._pyr), ofb200.ptr(coords_d), ofb200.ptr(out), ofb200.ptr(idx), ofb200.ptr(valid),
-                b, h, w, self.radius, ofb200.stream_ptr(),
-            )
-        ofb200.check(rc, "ofb_corr_lookup")
+        oshape = (b, lvls * d * d, h, w)
+        if out is not None and (tuple(out.shape) != oshape or out.dtype != torch.float32 or not out.is_cuda
+                                or not out.is_contiguous()):
+            raise RuntimeError(f"CorrBlock: out must be a contiguous fp32 CUDA tensor of shape {oshape}")
+        idx = valid = None
+        if self._handle is not None and torch.is_grad_enabled() and not return_index:
+            res = _LookupFn.apply(self, coords_d, self._handle)
+            if out is not None:
+                out.copy_(res.detach())                       # the preallocated buffer is filled, the graph keeps `res`
+            out = res
+        else:
+            with torch.cuda.device(self._dev):
+                if return_index:
+                    idx = torch.empty((b * h * w, lvls, 2, d), dtype=torch.int32, device=self._dev)
+                    valid = torch.empty((b * h * w, lvls, d * d), dtype=torch.uint8, device=self._dev)
+            out = self._lookup(coords_d, out, idx, valid)
         if on_host:
             out = out.cpu()
             idx = idx.cpu() if idx is not None else None
             valid = valid.cpu() if valid is not None else None
         return (out, idx, valid) if return_index else out
+
+    def _lookup(self, coords_d: Tensor, out: Optional[Tensor], idx: Optional[Tensor], valid: Optional[Tensor]) -> Tensor:
+        b, c, h, w = self._shape
+        d = 2 * self.radius + 1
+        with torch.cuda.device(self._dev):
+            if out is None:
+                out = torch.empty((b, self.num_levels * d * d, h, w), dtype=torch.float32, device=self._dev)
+            rc = ofb200.load().ofb_corr_lookup(
+                ctypes.byref(self._pyr), ofb200.ptr(coords_d), ofb200.ptr(out), ofb200.ptr(idx), ofb200.ptr(valid),
+                b, h, w, self.radius, ofb200.stream_ptr(),
+            )
+        ofb200.check(rc, "ofb_corr_lookup")
+        return out
+
+    def _alloc_grad_pyramid(self) -> None:
+        """Dense fp32 gradient levels (B*h*w, h_l*w_l), tight rows, zero-filled: the lookups' backwards accumulate
+        into them, _PyramidHandle.backward consumes and frees them."""
+        b, c, h, w = self._shape
+        desc = ofb200.Pyramid()
+        elems = (ctypes.c_int64 * ofb200.MAX_LEVELS)()
+        ofb200.check(ofb200.load().ofb_pyramid_layout(h, w, self.num_levels, 0, ctypes.byref(desc), ctypes.byref(elems)),
+                     "ofb_pyramid_layout")
+        desc.dtype = ofb200.DTYPE_F32
+        self._dpyr = []
+        for lvl in range(self.num_levels):
+            buf = torch.zeros(b * h * w * int(elems[lvl]), dtype=torch.float32, device=self._dev)
+            self._dpyr.append(buf)
+            desc.base[lvl] = buf.data_ptr()
+        self._dpyr_desc = desc
 
     @staticmethod
     def corr(fmap1: Tensor, fmap2: Tensor, **kwargs) -> Tensor:
