@@ -180,6 +180,45 @@ def bench_lookup_c4():
     return recs
 
 
+def bench_backward_c4():
+    """C4 backward kernels: lookup backward (one iteration into the fp32 gradient pyramid), convex-upsample backward."""
+    import ctypes
+    b, c, h, w = 16, 256, 47, 156
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    lib = ofb200.load()
+    desc = ofb200.Pyramid()
+    elems = (ctypes.c_int64 * ofb200.MAX_LEVELS)()
+    ofb200.check(lib.ofb_pyramid_layout(h, w, 4, 0, ctypes.byref(desc), ctypes.byref(elems)), "layout")
+    desc.dtype = ofb200.DTYPE_F32
+    bufs = [torch.zeros(b * h * w * int(elems[l]), device="cuda") for l in range(4)]
+    for l in range(4):
+        desc.base[l] = bufs[l].data_ptr()
+    base = torch.stack(torch.meshgrid(torch.arange(w, device="cuda"), torch.arange(h, device="cuda"), indexing="xy"), 0)[None].float()
+    coords = (base + 4 * torch.randn((b, 2, h, w), device="cuda", generator=gen)).contiguous()
+    d_out = torch.randn((b, 324, h, w), device="cuda", generator=gen)
+
+    def lk():
+        rc = lib.ofb_corr_lookup_backward_f32(ctypes.byref(desc), ofb200.ptr(coords), ofb200.ptr(d_out), b, h, w, 4, ofb200.stream_ptr())
+        assert rc == 0
+    ms = timeit(lk)
+    q = b * h * w
+    recs = [record("C4 B16 47x156 K3 lookup backward r=4, per iteration (fp32 gradient pyramid RMW)", ms,
+                   nbytes=q * (4 * 81 * 4 + 4 * 100 * 8 + 8))]
+    flow = torch.randn((b, 2, h, w), device="cuda", generator=gen)
+    mask = torch.randn((b, 576, h, w), device="cuda", generator=gen)
+    g_up = torch.randn((b, 2, 8 * h, 8 * w), device="cuda", generator=gen)
+    d_flow = torch.zeros_like(flow)
+    d_mask = torch.empty_like(mask)
+
+    def up():
+        rc = lib.ofb_convex_upsample_backward_f32(ofb200.ptr(flow), ofb200.ptr(mask), ofb200.ptr(g_up), ofb200.ptr(d_flow),
+                                                  ofb200.ptr(d_mask), b, h, w, ofb200.stream_ptr())
+        assert rc == 0
+    ms = timeit(up)
+    recs.append(record("C4 B16 47x156 K4b convex upsample backward", ms, nbytes=q * 4 * (576 * 2 + 128 + 4)))
+    return recs
+
+
 def bench_sequence_loss_c4(n_pred=12):
     """sequence_loss over 12 full-resolution predictions at the C4 (KITTI) size: 8 B/px per prediction + 12 B/px."""
     import ctypes
