@@ -98,7 +98,8 @@ def test_warp_options_golden(golden, mode, pad, ac):
             assert maxabs(out, ref) <= 1e-5, variant
 
 
-@pytest.mark.parametrize("shape,sigma", [((2, 3, 70, 130), 5.0), ((1, 3, 368, 496), 5.0), ((3, 5, 33, 257), 20.0), ((1, 1, 16, 64), 0.3)])
+@pytest.mark.parametrize("shape,sigma", [((2, 3, 70, 130), 5.0), ((1, 3, 368, 496), 5.0), ((3, 5, 33, 257), 20.0), ((1, 1, 16, 64), 0.3),
+                                         ((1, 2, 1, 7), 0.6), ((1, 3, 5, 1), 0.6), ((2, 1, 1, 1), 0.4)])
 @pytest.mark.parametrize("pad,ac", [("border", False), ("zeros", False), ("reflection", True)])
 def test_warp_vs_oracle(shape, sigma, pad, ac):
     from optical_flow import normalize, warp
@@ -137,8 +138,10 @@ def test_warp_backward_golden(golden, pad, ac):
     assert maxabs(N(flow.grad), want_w) <= 1e-5 * max(1.0, np.abs(want_w).max())
 
 
-@pytest.mark.parametrize("shape,sigma", [((2, 3, 70, 130), 5.0), ((1, 2, 368, 496), 30.0), ((3, 5, 33, 257), 2.0)])
-@pytest.mark.parametrize("pad,ac", [("border", False), ("zeros", False), ("reflection", True), ("border", True)])
+@pytest.mark.parametrize("shape,sigma", [((2, 3, 70, 130), 5.0), ((1, 2, 368, 496), 30.0), ((3, 5, 33, 257), 2.0),
+                                         ((1, 2, 1, 7), 2.0), ((1, 3, 5, 1), 2.0), ((2, 1, 2, 2), 0.5)])
+@pytest.mark.parametrize("pad,ac", [("border", False), ("zeros", False), ("reflection", True), ("border", True),
+                                    ("reflection", False), ("zeros", True)])
 def test_warp_backward_vs_oracle(shape, sigma, pad, ac):
     """Backward kernel against autograd through oracle/torch_port.py (pinned to the reference's gradients on CPU):
     both gradients, each alone, the fused pixel-flow variant, host tensors and the forward-with-mask form."""

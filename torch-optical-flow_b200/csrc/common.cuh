@@ -39,8 +39,9 @@ namespace ofb {
 // torch.linspace(-1, 1, n)[i] in fp32: step = 2/(n-1); symmetric halves, one fused op each
 // (same expression ATen's CPU and CUDA range factories evaluate; reference call sites
 // optical_flow/operator/operator.py:49-50).
+// a single-element linspace is its start value, -1 (torch.linspace(-1, 1, 1) == [-1])
 __device__ __forceinline__ float linspace_m1_p1(int i, int n, float step) {
-    return (i < n / 2) ? __fmaf_rn(step, (float)i, -1.0f) : __fmaf_rn(-step, (float)(n - 1 - i), 1.0f);
+    return (i < n / 2 || n == 1) ? __fmaf_rn(step, (float)i, -1.0f) : __fmaf_rn(-step, (float)(n - 1 - i), 1.0f);
 }
 __host__ __device__ __forceinline__ float linspace_step(int n) { return n > 1 ? 2.0f / (float)(n - 1) : 0.0f; }
 
