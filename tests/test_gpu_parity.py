@@ -951,7 +951,7 @@ def test_random_shapes_corr_block_and_lookup(seed, monkeypatch):
     assert maxabs(N(out), ref) <= tol(ref), info
 
 
-@pytest.mark.parametrize("seed", list(range(8)))
+@pytest.mark.parametrize("seed", list(range(12)))
 def test_random_shapes_streaming_kernels(seed):
     """Random shapes / options for warp (every kernel variant), resize, convex upsampling and the metric reductions
     against the oracle."""
@@ -961,7 +961,11 @@ def test_random_shapes_streaming_kernels(seed):
 
     r = rng(2000 + seed)
     b, c = int(r.integers(1, 4)), int(r.integers(1, 6))
-    h, w = int(r.integers(2, 90)), int(r.integers(2, 200))
+    h, w = int(r.integers(1, 90)), int(r.integers(1, 200))
+    if seed == 3:
+        h = 1
+    if seed == 5:
+        w = 1
     if seed % 2:
         w = (w + 3) // 4 * 4                                  # widths the TMA-window warp accepts
     pad = str(r.choice(["zeros", "border", "reflection"]))
