@@ -9,7 +9,11 @@ Tolerances (BASELINE.md section 5 / north_star):
   correlation pyramid (bf16 in, fp32 acc, bf16 stored) : rel-Frobenius <= 4e-3 per level and
                                             max-abs <= 4e-2 * rms vs the fp32 reference
   EPE sum / count                         : rel <= 1e-6 / exact
+  gradients (warp, upsample, sequence_loss, CorrBlock) : max-abs <= 1e-5 .. 5e-5 * |ref|_inf vs autograd through the
+                                            reference (golden) / oracle/torch_port.py
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -425,6 +429,16 @@ def test_corr_block_backward(golden):
         sum((blk(T(x)) * T(y)).sum() for x, y in zip(cs, ws)).backward()
         assert maxabs(N(g1.grad), c1.grad.numpy()) <= 5e-5 * np.abs(c1.grad.numpy()).max(), (b, c, h, w, lv, rad)
         assert maxabs(N(g2.grad), c2.grad.numpy()) <= 5e-5 * np.abs(c2.grad.numpy()).max(), (b, c, h, w, lv, rad)
+    # bf16 GEMM operands (fp32 accumulation) for the feature-map gradients: mixed-precision tolerance
+    os.environ["OFB200_BWD_GEMM"] = "bf16"
+    try:
+        h1, h2 = T(a1).requires_grad_(True), T(a2).requires_grad_(True)
+        blk = CorrBlock(h1, h2, num_levels=lv, radius=rad)
+        sum((blk(T(x)) * T(y)).sum() for x, y in zip(cs, ws)).backward()
+    finally:
+        del os.environ["OFB200_BWD_GEMM"]
+    for got, want in ((h1.grad, g1.grad), (h2.grad, g2.grad)):
+        assert float((got - want).norm() / want.norm()) <= 1e-2
     # only fmap2 requires grad; no_grad lookups stay forward-only
     g2 = T(a2).requires_grad_(True)
     blk = CorrBlock(T(a1), g2, num_levels=lv, radius=rad)

@@ -88,13 +88,19 @@ class _PyramidHandle(torch.autograd.Function):
                 for _ in range(blk.num_levels - 1):
                     cur = torch.nn.functional.avg_pool2d(cur, 2, stride=2)
                     levels.append(cur)
+            # GEMM precision: fp32 (default, matches the reference's fp32 autograd to 1e-5) or bf16 operands with
+            # fp32 accumulation (OFB200_BWD_GEMM=bf16: what a `precision: 16` run of the reference computes)
+            gemm_dt = torch.bfloat16 if os.environ.get("OFB200_BWD_GEMM", "fp32").lower() == "bf16" else torch.float32
+            f1g = f1.to(gemm_dt)
             d1 = torch.zeros_like(f1)
             d_levels = []
             for lvl, f2l in enumerate(levels):
                 hl, wl = f2l.shape[-2:]
-                dp = blk._dpyr[lvl].view(b, h * w, hl * wl)                          # (B, N, N_l), tight rows
-                d1.baddbmm_(f2l.detach().reshape(b, c, hl * wl), dp.transpose(1, 2), alpha=scale)
-                d_levels.append((torch.bmm(f1, dp) * scale).view(b, c, hl, wl))
+                dp = blk._dpyr[lvl].view(b, h * w, hl * wl).to(gemm_dt)              # (B, N, N_l), tight rows
+                f2g = f2l.detach().reshape(b, c, hl * wl).to(gemm_dt)
+                d1.add_(torch.bmm(f2g, dp.transpose(1, 2)).float(), alpha=scale)
+                d_levels.append((torch.bmm(f1g, dp).float() * scale).view(b, c, hl, wl))
+                blk._dpyr[lvl] = None                                               # free level by level
             d2 = torch.autograd.grad(levels, leaf, d_levels)[0]
             d1 = d1.view(b, c, h, w).to(fmap1.dtype)
             d2 = d2.to(fmap2.dtype)
