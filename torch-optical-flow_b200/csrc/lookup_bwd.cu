@@ -6,13 +6,15 @@
 // (raft.py:127), so only d / d pyramid is produced.
 //
 // thread = (query, level), lane <-> query (d_out reads are 128-byte rows).  A (query, level) slice is touched by
-// exactly one thread per launch, so the accumulation into the fp32 gradient pyramid is a plain read-modify-write
-// (no atomics); the 12 refinement iterations accumulate into the same buffer, launch after launch.
+// exactly one thread per launch, so the accumulation into the fp32 gradient pyramid needs no atomicity; it is
+// still issued as red.global.add.f32 (result unused): one fire-and-forget operation per element instead of a load
+// + store round trip (measured 0.75 -> 0.40 ms per iteration at C4).  The 12 refinement iterations accumulate
+// into the same buffer, launch after launch.
 //   * regular windows (taps on consecutive integer positions -- all but coordinates on rounding boundaries): the
 //     (2r+1)^2 gradients are pushed through the separable 2-tap filters in registers, one output row at a time:
 //       T[j][c]  = g[c][j] * w0x[c] + g[c-1][j] * w1x[c-1]            (x pass; the window is transposed: i moves x)
 //       dP[r][c] += T[r][c] * w0y[r] + T[r-1][c] * w1y[r-1]           (y pass)
-//     i.e. (2r+2)^2 read-modify-writes in 2r+2 short rows instead of 4 (2r+1)^2 scattered ones;
+//     i.e. (2r+2)^2 accumulations in 2r+2 short rows instead of 4 (2r+1)^2 scattered ones;
 //   * anything else: the direct 4-tap scatter.
 // The tap positions and weights replay the forward kernel's fp32 sequence (lookup.cu header).
 #include "common.cuh"
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(128) lookup_bwd_kernel(const BwdParams P, cons
                     if (j < D) v = tcur[c] * wy0[j < D ? j : 0];
                     if (j > 0) v = __fmaf_rn(tprev[c], wy1[j > 0 ? j - 1 : 0], v);
                     const int x = ax + c;
-                    if (x >= 0 && x < Wl) row[c] += v;
+                    if (x >= 0 && x < Wl) atomicAdd(row + c, v);
                 }
             }
 #pragma unroll
@@ -128,10 +130,10 @@ __global__ void __launch_bounds__(128) lookup_bwd_kernel(const BwdParams P, cons
             const bool iny0 = ty.i0 >= 0 && ty.i0 < Hl, iny1 = ty.i0 + 1 >= 0 && ty.i0 + 1 < Hl;
             float* r0 = slice + (long long)ty.i0 * pitch + tx.i0;
             float* r1 = r0 + pitch;
-            if (iny0 && inx0) r0[0] += g * tx.w0 * ty.w0;
-            if (iny0 && inx1) r0[1] += g * tx.w1 * ty.w0;
-            if (iny1 && inx0) r1[0] += g * tx.w0 * ty.w1;
-            if (iny1 && inx1) r1[1] += g * tx.w1 * ty.w1;
+            if (iny0 && inx0) atomicAdd(r0, g * tx.w0 * ty.w0);
+            if (iny0 && inx1) atomicAdd(r0 + 1, g * tx.w1 * ty.w0);
+            if (iny1 && inx0) atomicAdd(r1, g * tx.w0 * ty.w1);
+            if (iny1 && inx1) atomicAdd(r1 + 1, g * tx.w1 * ty.w1);
         }
     }
 }
