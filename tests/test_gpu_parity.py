@@ -186,6 +186,20 @@ def test_warp_backward_vs_oracle(shape, sigma, pad, ac):
     assert not hf.grad.is_cuda and maxabs(hf.grad.numpy(), want_f) <= tol_f
 
 
+def test_scale_normalize_backward():
+    """scale / normalize / denormalize are differentiable: the gradient is the same per-channel multiply."""
+    from optical_flow import denormalize, normalize, scale
+
+    flow = torch.randn(2, 2, 9, 14, device="cuda", requires_grad=True)
+    wgt = torch.randn(2, 2, 9, 14, device="cuda")
+    (normalize(flow) * wgt).sum().backward()
+    fac = torch.tensor([2.0 / 13, 2.0 / 8], device="cuda").view(1, 2, 1, 1)
+    assert torch.allclose(flow.grad, wgt * fac, rtol=1e-6, atol=0)
+    flow.grad = None
+    (denormalize(scale(flow, (3.0, -0.5))) * wgt).sum().backward()
+    assert torch.allclose(flow.grad, wgt * torch.tensor([3.0 * 6.5, -0.5 * 4.0], device="cuda").view(1, 2, 1, 1), rtol=1e-6, atol=0)
+
+
 def test_warp_channels_last_and_host_tensors():
     from optical_flow import warp
 
@@ -446,6 +460,64 @@ def test_corr_block_backward(golden):
         assert not blk(T(cs[0])).requires_grad
     (blk(T(cs[0])) * T(ws[0])).sum().backward()
     assert g2.grad is not None and bool(torch.isfinite(g2.grad).all())
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_training_step_composes(dt):
+    """A miniature RAFT training step through every differentiable op of the package -- CorrBlock, three lookups
+    feeding a small update head, convex upsampling, sequence_loss, and a photometric warp term -- against the same
+    computation through oracle/torch_port.py on the CPU: loss value and the gradients of the feature maps, the
+    head's weights and the image."""
+    from model import CorrBlock, sequence_loss, upsample_flow
+    from optical_flow import warp
+    from oracle import torch_port as tp
+
+    torch.manual_seed(5)
+    b, c, h, w, iters = 1, 64, 16, 24, 3
+    f1, f2 = torch.randn(b, c, h, w), torch.randn(b, c, h, w)
+    img = torch.rand(b, 3, 8 * h, 8 * w)
+    head_flow = 0.02 * torch.randn(2, 4 * 81, 1, 1)
+    head_mask = 0.05 * torch.randn(576, 4 * 81, 1, 1)
+    gt = 4.0 * torch.randn(b, 2, 8 * h, 8 * w)
+    valid = (torch.rand(b, 8 * h, 8 * w) > 0.2).float()
+    base = torch.stack(torch.meshgrid(torch.arange(w), torch.arange(h), indexing="xy"), 0)[None].float()
+
+    def step(dev, corr_fn, lookup_fn, up_fn, loss_fn, warp_fn, norm_fn):
+        leaves = [t.clone().to(dev).requires_grad_(True) for t in (f1, f2, head_flow, head_mask, img)]
+        a1, a2, wf, wm, im = leaves
+        state = corr_fn(a1, a2)
+        coords = base.to(dev).clone()
+        preds = []
+        for _ in range(iters):
+            corr = lookup_fn(state, coords.detach())
+            delta = torch.nn.functional.conv2d(corr, wf)
+            mask = torch.nn.functional.conv2d(corr, wm)
+            coords = coords + delta
+            preds.append(up_fn(coords - base.to(dev), mask))
+        loss, _ = loss_fn(preds, gt.to(dev), valid.to(dev))
+        photo = ((warp_fn(im, norm_fn(preds[-1])) - im) ** 2).mean()
+        total = loss + 0.1 * photo
+        total.backward()
+        return float(total.detach()), [t.grad.cpu() for t in leaves]
+
+    want_loss, want = step("cpu", lambda x, y: tp.corr_pyramid(x, y, 4), lambda p, cds: tp.corr_lookup(p, cds, 4),
+                           tp.upsample_flow, lambda p, g_, v: tp.sequence_loss(p, g_, v), tp.warp, tp.normalize)
+    from optical_flow import normalize
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False                  # the head's convolutions are torch glue: keep them fp32
+    try:
+        got_loss, got = step("cuda", lambda x, y: CorrBlock(x, y, num_levels=4, radius=4, pyramid_dtype=dt),
+                             lambda blk, cds: blk(cds), upsample_flow, lambda p, g_, v: sequence_loss(p, g_, v), warp, normalize)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    # fp32 volume: fp32 noise through three refinement iterations; bf16 volume (the product default): the loss agrees
+    # to mixed-precision accuracy, the gradients to a few per cent (sign(pred - gt) flips where the two runs' flows
+    # straddle the ground truth)
+    tol_loss, tol_grad = (1e-4, 2e-3) if dt == torch.float32 else (2e-3, 5e-2)
+    assert abs(got_loss - want_loss) <= tol_loss * abs(want_loss)
+    for name, gg, ww in zip(("fmap1", "fmap2", "head_flow", "head_mask", "image"), got, want):
+        rel = float((gg - ww).norm() / ww.norm())
+        assert rel <= tol_grad, (name, rel)
 
 
 def test_upsample_and_sequence_loss_backward(golden):

@@ -147,7 +147,12 @@ def scale(flow: Tensor, factor: Union[float, Tuple[float, float]] = 1.0) -> Tens
         ofb200.check(rc, "ofb_scale_flow_f32")
         return out
 
-    return _run(run, "scale", flow)
+    def backward(saved, grad_out: Tensor, needs):
+        """d scale / d flow is the same per-channel multiply applied to the incoming gradient."""
+        with torch.cuda.device(grad_out.device):
+            return (run(grad_out),)
+
+    return _run(run, "scale", flow, bwd=backward)
 
 
 def _resize_raw(x: Tensor, size: Tuple[int, int], align_corners: bool, mul_x: float, mul_y: float, name: str) -> Tensor:
