@@ -100,6 +100,12 @@ int ofb_scale_flow_f32(const float* flow, float* out, int B, int64_t HW, float f
  * ------------------------------------------------------------------------------------- */
 int ofb_resize_bilinear_f32(const float* in, float* out, int N, int C, int H, int W, int Ho, int Wo,
                             int align_corners, float mul_x, float mul_y, void* stream);
+/* Its adjoint (autograd through F.interpolate + scale, operator.py:112-113; through upflow8,
+ * utils.py:91): d_out (N,C,Ho,Wo) is scattered into d_in (N,C,H,W), which is ACCUMULATED into
+ * (zero it first). */
+int ofb_resize_bilinear_backward_f32(const float* d_out, float* d_in, int N, int C, int H, int W,
+                                     int Ho, int Wo, int align_corners, float mul_x, float mul_y,
+                                     void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * K4b  convex 8x flow upsampling.  Replaces RAFT.upsample_flow

@@ -35,6 +35,20 @@ def normalize(flow):
     return flow * fac.view(1, 2, 1, 1)
 
 
+def resize(flow, size):
+    """operator.py:85-114 -- F.interpolate(bilinear, align_corners=False) then scale by (W'/W, H'/H)."""
+    h, w = flow.shape[-2:]
+    out = F.interpolate(flow, size=size, mode="bilinear")
+    fac = torch.tensor([size[1] / w, size[0] / h], dtype=flow.dtype, device=flow.device)
+    return out * fac.view(1, 2, 1, 1)
+
+
+def upflow8(flow):
+    """methods/raft/model/utils.py:89-91 -- 8 * F.interpolate(bilinear, align_corners=True)."""
+    h, w = flow.shape[-2:]
+    return 8 * F.interpolate(flow, size=(8 * h, 8 * w), mode="bilinear", align_corners=True)
+
+
 def bilinear_sampler(img, coords):
     """methods/raft/model/utils.py:64-80 -- pixel coordinates -> [-1, 1] -> grid_sample(align_corners=True)."""
     h, w = img.shape[-2:]

@@ -186,6 +186,29 @@ def test_warp_backward_vs_oracle(shape, sigma, pad, ac):
     assert not hf.grad.is_cuda and maxabs(hf.grad.numpy(), want_f) <= tol_f
 
 
+@pytest.mark.parametrize("shape,size", [((2, 2, 9, 14), (20, 31)), ((1, 2, 40, 64), (17, 23)), ((3, 2, 5, 7), (5, 7)), ((1, 2, 1, 6), (3, 1))])
+def test_resize_and_upflow8_backward(shape, size):
+    """resize / upflow8 gradients against autograd through the ATen ops the reference calls."""
+    from model import upflow8
+    from optical_flow import resize
+    from oracle import torch_port as tp
+
+    r = rng(61)
+    flow = r.standard_normal(shape).astype(np.float32)
+    wr = r.standard_normal((shape[0], 2) + size).astype(np.float32)
+    cf = torch.from_numpy(flow).requires_grad_(True)
+    (tp.resize(cf, size) * torch.from_numpy(wr)).sum().backward()
+    gf = T(flow).requires_grad_(True)
+    (resize(gf, size=size) * T(wr)).sum().backward()
+    assert maxabs(N(gf.grad), cf.grad.numpy()) <= 1e-5 * max(1.0, np.abs(cf.grad.numpy()).max())
+    wu = r.standard_normal((shape[0], 2, 8 * shape[2], 8 * shape[3])).astype(np.float32)
+    cf = torch.from_numpy(flow).requires_grad_(True)
+    (tp.upflow8(cf) * torch.from_numpy(wu)).sum().backward()
+    gf = T(flow).requires_grad_(True)
+    (upflow8(gf) * T(wu)).sum().backward()
+    assert maxabs(N(gf.grad), cf.grad.numpy()) <= 2e-5 * max(1.0, np.abs(cf.grad.numpy()).max())
+
+
 def test_scale_normalize_backward():
     """scale / normalize / denormalize are differentiable: the gradient is the same per-channel multiply."""
     from optical_flow import denormalize, normalize, scale
@@ -260,7 +283,8 @@ def test_warp_errors():
     with pytest.raises(NotImplementedError):                      # nearest has no backward kernel
         warp(x.requires_grad_(), f, mode="nearest").sum().backward()
     with pytest.raises(NotImplementedError):                      # forward-only ops say so instead of returning zeros
-        resize(f.clone().requires_grad_(), scale_factor=2.0).sum().backward()
+        from model import bilinear_sampler
+        bilinear_sampler(x.detach().clone().requires_grad_(), torch.zeros(1, 2, 2, 2, device="cuda")).sum().backward()
 
 
 def test_warp_grid_and_integrate_golden(golden):

@@ -67,6 +67,29 @@ __global__ void __launch_bounds__(256) resize_kernel(const float* __restrict__ i
     }
 }
 
+// Adjoint of resize_kernel (what autograd computes through F.interpolate + scale, operator.py:112-113, and through
+// 8 * F.interpolate in upflow8): every output gradient is scattered to its four source pixels with the forward
+// weights times the magnitude factor.  One thread per output pixel, red.global.add.f32 into d_in (small).
+__global__ void __launch_bounds__(256) resize_bwd_kernel(const float* __restrict__ d_out, float* __restrict__ d_in,
+                                                         int NC, int H, int W, int Ho, int Wo, int ac, float rh, float rw,
+                                                         float mul_x, float mul_y) {
+    const size_t total = (size_t)NC * Ho * Wo;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int ox = (int)(t % Wo);
+        const int oy = (int)((t / Wo) % Ho);
+        const int nc = (int)(t / ((size_t)Wo * Ho));
+        const float g = __fmul_rn(__ldg(d_out + t), (nc & 1) ? mul_y : mul_x);
+        int y0, y1, x0, x1; float ly0, ly1, lx0, lx1;
+        src_index(rh, oy, H, Ho, ac != 0, y0, y1, ly0, ly1);
+        src_index(rw, ox, W, Wo, ac != 0, x0, x1, lx0, lx1);
+        float* dst = d_in + (size_t)nc * H * W;
+        atomicAdd(dst + (size_t)y0 * W + x0, ly0 * lx0 * g);
+        atomicAdd(dst + (size_t)y0 * W + x1, ly0 * lx1 * g);
+        atomicAdd(dst + (size_t)y1 * W + x0, ly1 * lx0 * g);
+        atomicAdd(dst + (size_t)y1 * W + x1, ly1 * lx1 * g);
+    }
+}
+
 __global__ void __launch_bounds__(256) scale_flow_kernel(const float* __restrict__ in, float* __restrict__ out, int B,
                                                          int64_t HW, float fx, float fy) {
     const int64_t total = (int64_t)B * 2 * HW;
@@ -98,6 +121,29 @@ OFB_API int ofb_resize_bilinear_f32(const float* in, float* out, int N, int C, i
     const int vec_ok = (Wo % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     resize_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in, out, N * C, H, W, Ho, Wo, align_corners, rh, rw, mul_x,
                                                              mul_y, vec_ok);
+    OFB_LAUNCH_CHECK();
+    return OFB_OK;
+}
+
+OFB_API int ofb_resize_bilinear_backward_f32(const float* d_out, float* d_in, int N, int C, int H, int W, int Ho, int Wo,
+                                             int align_corners, float mul_x, float mul_y, void* stream) {
+    if (!d_out || !d_in || N < 0 || C < 0 || H <= 0 || W <= 0 || Ho < 0 || Wo < 0) return OFB_EINVAL;
+    if ((C & 1) && (mul_x != mul_y)) return OFB_EINVAL;
+    const size_t total = (size_t)N * C * Ho * Wo;
+    if (total == 0) return OFB_OK;
+    float rh, rw;
+    if (align_corners) {
+        rh = Ho > 1 ? (float)(H - 1) / (float)(Ho - 1) : 0.0f;
+        rw = Wo > 1 ? (float)(W - 1) / (float)(Wo - 1) : 0.0f;
+    } else {
+        rh = (float)H / (float)Ho;
+        rw = (float)W / (float)Wo;
+    }
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = (size_t)ofb_num_sms() * 32;
+    if (blocks > cap) blocks = cap;
+    resize_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(d_out, d_in, N * C, H, W, Ho, Wo, align_corners, rh,
+                                                                      rw, mul_x, mul_y);
     OFB_LAUNCH_CHECK();
     return OFB_OK;
 }

@@ -53,6 +53,7 @@ SIGNATURES = {
     "ofb_warp_backward_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _f, _vp]),
     "ofb_warp_grid_f32": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "ofb_scale_flow_f32": (_i, [_vp, _vp, _i, _i64, _f, _f, _vp]),
+    "ofb_resize_bilinear_backward_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp]),
     "ofb_resize_bilinear_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp]),
     "ofb_convex_upsample_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "ofb_epe_reduce_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),

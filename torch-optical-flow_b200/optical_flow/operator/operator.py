@@ -169,7 +169,18 @@ def _resize_raw(x: Tensor, size: Tuple[int, int], align_corners: bool, mul_x: fl
         ofb200.check(rc, "ofb_resize_bilinear_f32")
         return out
 
-    return _run(run, name, x)
+    def backward(saved, grad_out: Tensor, needs):
+        """Adjoint of the bilinear resize: scatter the output gradient with the forward weights."""
+        with torch.cuda.device(grad_out.device):
+            d_in = torch.zeros((n, c, h, w), dtype=torch.float32, device=grad_out.device)
+            rc = ofb200.load().ofb_resize_bilinear_backward_f32(
+                ofb200.ptr(grad_out.contiguous()), ofb200.ptr(d_in), n, c, h, w, ho, wo, int(align_corners), float(mul_x),
+                float(mul_y), ofb200.stream_ptr(),
+            )
+            ofb200.check(rc, "ofb_resize_bilinear_backward_f32")
+        return (d_in,)
+
+    return _run(run, name, x, bwd=backward)
 
 
 def resize(
