@@ -541,6 +541,7 @@ def test_training_step_composes(dt):
     assert abs(got_loss - want_loss) <= tol_loss * abs(want_loss)
     for name, gg, ww in zip(("fmap1", "fmap2", "head_flow", "head_mask", "image"), got, want):
         rel = float((gg - ww).norm() / ww.norm())
+        print(f"training step [{dt}] {name}: rel grad diff {rel:.2e}; loss diff {abs(got_loss - want_loss) / abs(want_loss):.2e}")
         assert rel <= tol_grad, (name, rel)
 
 

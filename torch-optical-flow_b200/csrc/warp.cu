@@ -5,15 +5,14 @@
 //   out[b,c,i,j] = grid_sample(frame[b,c], (gx,gy), mode, padding_mode, align_corners)
 // Neither the base grid nor grid+flow is ever materialised.
 //
-// Two bilinear NCHW kernels:
-//   * direct : one thread per output pixel, 4 read-only gathers per channel.  With a random
-//     flow every warp-wide gather touches up to 32 cache lines, so this one is bound by L1
-//     wavefronts, not HBM.
-//   * staged : one CTA per 64x16 output tile.  Pass 1 computes every pixel's source position
-//     and the CTA-wide bounding box of the taps; pass 2 copies that neighbourhood (clamped to
-//     tile +- R) into shared memory with 16-byte cp.async; pass 3 gathers from shared memory
-//     (global fallback for the rare tap outside the staged window).  HBM sees each frame
-//     line about once; the gather runs at shared-memory speed.
+// Bilinear NCHW kernels (variant argument of ofb_warp_f32; all produce the same bits):
+//   * rows (default): lane <-> column, a thread owns 2 consecutive rows of its column, coordinates / weights /
+//     tap offsets computed once per pixel and reused per channel; interior pixels take a predicate-free channel
+//     loop with every gather in flight before the first FMA.  32 registers -> 64 resident warps per SM: the
+//     kernel is bound by latency and instruction issue, not by HBM.
+//   * direct: one thread per output pixel, grid-stride; also serves nearest mode and NHWC frames.
+//   * staged: one CTA per 64x16 output tile, bounding box of the taps copied to shared memory with cp.async.
+//   * TMA window (warp_tma.cu): persistent CTAs, the tile's neighbourhood arrives as 3-D TMA boxes.
 // HBM roofline: 4*(C + 2 + C) bytes per pixel (+1 for the u8 mask).
 #include <cstdlib>
 
