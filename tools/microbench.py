@@ -219,6 +219,42 @@ def bench_backward_c4():
     return recs
 
 
+def bench_corr_train_c4(b=4, iters=12):
+    """CorrBlock forward + backward at the KITTI size: build, `iters` lookups, then the backward pass (lookup backward
+    kernels into the fp32 gradient pyramid, feature-map gradients through the library GEMMs), fp32 and bf16 GEMMs."""
+    import os
+    from model import CorrBlock
+    c, h, w = 256, 47, 156
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    f1 = torch.randn((b, c, h, w), device="cuda", generator=gen)
+    f2 = torch.randn((b, c, h, w), device="cuda", generator=gen)
+    base = torch.stack(torch.meshgrid(torch.arange(w, device="cuda"), torch.arange(h, device="cuda"), indexing="xy"), 0)[None].float()
+    coords = [(base + 3 * torch.randn((b, 2, h, w), device="cuda", generator=gen)).contiguous() for _ in range(iters)]
+    wts = [torch.randn((b, 324, h, w), device="cuda", generator=gen) for _ in range(iters)]
+    recs = []
+    for mode in ("fp32", "bf16"):
+        os.environ["OFB200_BWD_GEMM"] = mode
+        times = {"fwd": [], "bwd": []}
+        for rep in range(4):
+            a1, a2 = f1.clone().requires_grad_(True), f2.clone().requires_grad_(True)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            torch.cuda.synchronize()
+            ev[0].record()
+            blk = CorrBlock(a1, a2, num_levels=4, radius=4)
+            total = sum((blk(cd) * wt).sum() for cd, wt in zip(coords, wts))
+            ev[1].record()
+            total.backward()
+            ev[2].record()
+            torch.cuda.synchronize()
+            if rep:
+                times["fwd"].append(ev[0].elapsed_time(ev[1]))
+                times["bwd"].append(ev[1].elapsed_time(ev[2]))
+        recs.append({"kernel": f"C4 B{b} 47x156 CorrBlock train step, {iters} lookups, d-fmap GEMMs in {mode}",
+                     "fwd_ms": round(min(times["fwd"]), 3), "bwd_ms": round(min(times["bwd"]), 3)})
+    del os.environ["OFB200_BWD_GEMM"]
+    return recs
+
+
 def bench_sequence_loss_c4(n_pred=12):
     """sequence_loss over 12 full-resolution predictions at the C4 (KITTI) size: 8 B/px per prediction + 12 B/px."""
     import ctypes
