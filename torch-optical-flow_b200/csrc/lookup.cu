@@ -310,13 +310,17 @@ __global__ void __launch_bounds__(128) lookup_tile_kernel(const LookupParams P, 
 #pragma unroll
         for (int i = 0; i < D; ++i) acc[k][i] = 0.0f;
 
-    // Window rows -> this thread's private shared-memory slots with cp.async (16 bytes each, zero-filled when
-    // the chunk is outside the slice): every load of the window is in flight at once and none of them holds a
-    // register.  Slot (row r, chunk c) of thread t lives at ((r*3 + c) * blockDim + t) * 16: a warp's accesses
-    // are 512 contiguous bytes, conflict-free.
+    // Window rows -> this thread's private shared-memory slots with cp.async (zero-filled when the chunk is outside
+    // the slice): every load of the window is in flight at once and none of them holds a register.  Chunks 0 and 1
+    // are 16-byte slots at ((r*2 + c) * blockDim + t) * 16; of chunk 2 only the first 4 elements can fall inside
+    // the window (s + WIN - 1 <= 17), so it gets an 8-byte slot at CK2_BASE + (r * blockDim + t) * 8.  A warp's
+    // accesses are contiguous and conflict-free; 40 bytes per row and thread keep 4 CTAs (16 warps) on an SM.
     extern __shared__ __align__(16) uint8_t win_smem[];
-    const uint32_t my_slot = (uint32_t)__cvta_generic_to_shared(win_smem) + threadIdx.x * 16u;
+    const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(win_smem);
+    const uint32_t my_slot = smem0 + threadIdx.x * 16u;
     const uint32_t slot_stride = blockDim.x * 16u;
+    const uint32_t my_slot2 = smem0 + (uint32_t)(WIN * 2) * slot_stride + threadIdx.x * 8u;
+    const uint32_t slot2_stride = blockDim.x * 8u;
     {
         const long long cstep = P.blocked ? P.blk_stride : 8;
 #pragma unroll
@@ -328,11 +332,17 @@ __global__ void __launch_bounds__(128) lookup_tile_kernel(const LookupParams P, 
                 ? slice + ((long long)(y >> 2) * (pitch >> 3) + (xa >> 3)) * P.blk_stride + (y & 3) * 8
                 : slice + (long long)y * pitch + xa;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const bool ok = rok && (c == 0 ? ck0 : c == 1 ? ck1 : ck2);
+            for (int c = 0; c < 2; ++c) {
+                const bool ok = rok && (c == 0 ? ck0 : ck1);
                 const void* src = ok ? (const void*)(row + c * cstep) : (const void*)slice;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(my_slot + (uint32_t)(r * 3 + c) * slot_stride),
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(my_slot + (uint32_t)(r * 2 + c) * slot_stride),
                              "l"(src), "r"(ok ? 16 : 0) : "memory");
+            }
+            {
+                const bool ok = rok && ck2;
+                const void* src = ok ? (const void*)(row + 2 * cstep) : (const void*)slice;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(my_slot2 + (uint32_t)r * slot2_stride),
+                             "l"(src), "r"(ok ? 8 : 0) : "memory");
             }
             // one commit group per GR rows: the filter below starts on the first rows while the rest are in flight
             if (r % GR == GR - 1 || r == WIN - 1) asm volatile("cp.async.commit_group;" ::: "memory");
@@ -348,12 +358,13 @@ __global__ void __launch_bounds__(128) lookup_tile_kernel(const LookupParams P, 
             else if (pending == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
             else asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
-        uint32_t w[12];
+        uint32_t w[10];
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
+        for (int c = 0; c < 2; ++c)
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                          : "=r"(w[4 * c]), "=r"(w[4 * c + 1]), "=r"(w[4 * c + 2]), "=r"(w[4 * c + 3])
-                         : "r"(my_slot + (uint32_t)(r * 3 + c) * slot_stride));
+                         : "r"(my_slot + (uint32_t)(r * 2 + c) * slot_stride));
+        asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(w[8]), "=r"(w[9]) : "r"(my_slot2 + (uint32_t)r * slot2_stride));
         // ---- realign: drop s leading elements (word shifts by 1 and 2, then a half-word funnel shift)
         uint32_t t1[9], t2[NW + 1], v[NW];
 #pragma unroll
@@ -465,14 +476,14 @@ OFB_API int ofb_corr_lookup(const ofb_pyramid* pyr, const float* coords, float* 
         tile_ok = (P.pitch[l] % 8 == 0) && (P.q_stride[l] % 8 == 0) && ((reinterpret_cast<uintptr_t>(P.base[l]) & 15) == 0);
     if (tile_ok) {
         const int threads = 32 * pyr->levels;
-        const size_t wsm = (size_t)(2 * radius + 3) * 3 * threads * 16;           // window slots: rows x 3 chunks x 16 B
+        const size_t wsm = (size_t)(2 * radius + 3) * threads * 40;               // window slots: rows x (16 + 16 + 8) B
         static int gr = 0;                                 // window rows per cp.async commit group: 3 (measured ~2 % faster
         if (!gr) {                                         // than one group for the whole window); OFB_LOOKUP_GR=16 for A/B
             const char* e = getenv("OFB_LOOKUP_GR");
             gr = (e && atoi(e) == 16) ? 16 : 3;
-            OFB_CUDA(cudaFuncSetAttribute(lookup_tile_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 11 * 3 * 128 * 16));
-            OFB_CUDA(cudaFuncSetAttribute(lookup_tile_kernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 11 * 3 * 128 * 16));
-            OFB_CUDA(cudaFuncSetAttribute(lookup_tile_kernel<3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 3 * 128 * 16));
+            OFB_CUDA(cudaFuncSetAttribute(lookup_tile_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 11 * 128 * 40));
+            OFB_CUDA(cudaFuncSetAttribute(lookup_tile_kernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 11 * 128 * 40));
+            OFB_CUDA(cudaFuncSetAttribute(lookup_tile_kernel<3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 128 * 40));
         }
         if (radius == 4 && gr == 3) lookup_tile_kernel<4, 3><<<(int)blocks, threads, wsm, st>>>(P, coords, out, idx_or_null, valid_or_null);
         else if (radius == 4) lookup_tile_kernel<4, 16><<<(int)blocks, threads, wsm, st>>>(P, coords, out, idx_or_null, valid_or_null);
