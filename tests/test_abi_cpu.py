@@ -93,3 +93,31 @@ def test_reference_assertion_behaviour():
         scale(torch.zeros(1, 2, 4, 4), (1.0, 2.0, 3.0))
     with pytest.raises(AssertionError):
         integrate(torch.zeros(1, 2, 4, 4))
+
+
+def test_pair_arena_layout_cpu():
+    """ofb200.runner.PairArena (host logic, no GPU): every field is a view of one (pairs, floats_per_pair) buffer at a
+    256-byte aligned offset, with the field's usual shape; a pair's fields are contiguous in memory so a micro-batch
+    is one slice of rows."""
+    import torch
+
+    from ofb200.runner import FIELDS, PairArena
+
+    pairs, c, h, w, iters = 3, 4, 5, 6, 2
+    g = torch.Generator().manual_seed(0)
+    batch = {"fmap1": torch.randn(pairs, c, h, w, generator=g), "fmap2": torch.randn(pairs, c, h, w, generator=g),
+             "coords": torch.randn(iters, pairs, 2, h, w, generator=g), "flow_lo": torch.randn(pairs, 2, h, w, generator=g),
+             "up_mask": torch.randn(pairs, 576, h, w, generator=g), "frame": torch.rand(pairs, 3, 8 * h, 8 * w, generator=g),
+             "target": torch.randn(pairs, 2, 8 * h, 8 * w, generator=g), "valid": torch.rand(pairs, 8 * h, 8 * w, generator=g)}
+    arena = PairArena(pairs, PairArena.shapes_of(batch)).fill(batch)
+    assert arena.buf.shape == (pairs, arena.pair_floats) and arena.pair_floats % PairArena.ALIGN == 0
+    for k in FIELDS:
+        assert arena.offsets[k] % PairArena.ALIGN == 0
+        assert arena[k].shape == batch[k].shape and torch.equal(arena[k], batch[k])
+        assert arena[k].data_ptr() == arena.buf.data_ptr() + 4 * arena.offsets[k]          # a view, not a copy
+    # a micro-batch is a row range: its views see the same values
+    for k in FIELDS:
+        sub = arena.view(k, 1, 3)
+        want = batch[k][:, 1:3] if k == "coords" else batch[k][1:3]
+        assert torch.equal(sub, want)
+    assert arena.payload_bytes_per_pair == 4 * sum(batch[k].numel() for k in FIELDS) // pairs

@@ -486,6 +486,35 @@ def test_corr_block_backward(golden):
     assert g2.grad is not None and bool(torch.isfinite(g2.grad).all())
 
 
+def test_host_staged_runner_arena_matches_dict():
+    """HostStagedRunner: a pinned pair-major arena (one DMA per micro-batch) gives the same EPE as the per-field
+    staging of a dict of pinned tensors and as the device-resident pass, for micro-batches of 1 and 2 pairs."""
+    from ofb200.runner import FIELDS, HostStagedRunner, PairArena, hot_path
+    from optical_flow.metrics import AverageEndPointError
+
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    pairs, c, h, w, iters = 3, 64, 16, 24, 2
+    rn = lambda *s: torch.randn(s, device="cuda", generator=gen)
+    base = torch.stack(torch.meshgrid(torch.arange(w, device="cuda"), torch.arange(h, device="cuda"), indexing="xy"), 0).float()
+    batch = {"fmap1": rn(pairs, c, h, w), "fmap2": rn(pairs, c, h, w),
+             "coords": (base[None, None] + 2 * rn(iters, pairs, 2, h, w)).contiguous(), "flow_lo": rn(pairs, 2, h, w),
+             "up_mask": rn(pairs, 576, h, w), "frame": torch.rand((pairs, 3, 8 * h, 8 * w), device="cuda", generator=gen),
+             "target": 5 * rn(pairs, 2, 8 * h, 8 * w), "valid": (torch.rand((pairs, 8 * h, 8 * w), device="cuda", generator=gen) > 0.2).float()}
+    m0 = AverageEndPointError()
+    hot_path(batch, m0)
+    want = float(m0.compute())
+    arena = PairArena(pairs, PairArena.shapes_of(batch), pin=True).fill(batch)
+    for k in FIELDS:
+        assert arena[k].shape == batch[k].shape and torch.equal(arena[k], batch[k].cpu())
+    host = {k: batch[k].cpu().pin_memory() for k in FIELDS}
+    for micro in (1, 2):
+        for src in (arena, host):
+            runner = HostStagedRunner(torch.device("cuda", 0), micro)
+            got = runner.run(src, AverageEndPointError())
+            assert abs(got - want) <= 1e-6 * abs(want), (micro, type(src).__name__)
+            assert runner.h2d_bytes >= sum(batch[k].numel() * 4 for k in FIELDS) and runner.d2h_bytes == 16
+
+
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
 def test_training_step_composes(dt):
     """A miniature RAFT training step through every differentiable op of the package -- CorrBlock, three lookups

@@ -98,10 +98,64 @@ def hot_path(batch: Dict[str, Tensor], metric: AverageEndPointError, timers: Opt
 LAUNCHES_PER_PASS = lambda iters: 5 + iters + 1 + 1 + 1  # noqa: E731  (prep x3, pyramid x2, lookups, upsample, warp, epe)
 
 
+class PairArena:
+    """Pair-major staging memory: one fp32 buffer of shape (pairs, floats_per_pair) in which every field of a pair
+    sits at a fixed, 256-byte aligned offset; `arena[name]` is a strided VIEW with the field's usual shape
+    ((pairs, ...), and (iters, pairs, 2, h, w) for `coords`).  A producer (data loader, upstream network) fills the
+    views of a pinned host arena; HostStagedRunner then moves a whole micro-batch -- all eight fields -- with ONE
+    host->device DMA into a device arena of the same layout instead of one copy per field and per iteration
+    (19 copies per pair at the bench shape, each paying its launch + DMA start-up)."""
+
+    ALIGN = 64   # floats
+
+    def __init__(self, pairs: int, shapes: Dict[str, tuple], device=None, pin: bool = False) -> None:
+        """shapes[name] = the field's per-pair shape; `coords` as (iters, 2, h, w)."""
+        self.pairs, self.shapes, self.offsets = pairs, dict(shapes), {}
+        off = 0
+        for k in FIELDS:
+            self.offsets[k] = off
+            n = 1
+            for d in shapes[k]:
+                n *= int(d)
+            off += (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.pair_floats = off
+        self.payload_bytes_per_pair = 4 * sum(int(torch.Size(shapes[k]).numel()) for k in FIELDS)
+        if device is None:
+            self.buf = torch.empty((pairs, off), dtype=torch.float32, pin_memory=pin)
+        else:
+            self.buf = torch.empty((pairs, off), dtype=torch.float32, device=device)
+
+    @staticmethod
+    def shapes_of(batch: Dict[str, Tensor]) -> Dict[str, tuple]:
+        """Per-pair shapes of an ordinary batch dict (coords (iters, pairs, 2, h, w) -> (iters, 2, h, w))."""
+        out = {}
+        for k in FIELDS:
+            sh = tuple(batch[k].shape)
+            out[k] = (sh[0],) + sh[2:] if k == "coords" else sh[1:]
+        return out
+
+    def view(self, name: str, lo: int = 0, hi: Optional[int] = None) -> Tensor:
+        hi = self.pairs if hi is None else hi
+        sh = self.shapes[name]
+        n = int(torch.Size(sh).numel())
+        flat = self.buf[lo:hi, self.offsets[name]:self.offsets[name] + n]
+        v = flat.view(hi - lo, *sh)
+        return v.transpose(0, 1) if name == "coords" else v
+
+    def __getitem__(self, name: str) -> Tensor:
+        return self.view(name)
+
+    def fill(self, batch: Dict[str, Tensor]) -> "PairArena":
+        for k in FIELDS:
+            self[k].copy_(batch[k])
+        return self
+
+
 class HostStagedRunner:
     """Runs the pass on PINNED HOST batches: micro-batches are copied on a side stream into two
     alternating device slots while the previous micro-batch computes; the EPE state is read back at the
-    end.  This is the end-to-end entry point bench.py times (`e2e`)."""
+    end.  This is the end-to-end entry point bench.py times (`e2e`).  `run` takes either a dict of pinned
+    tensors (one copy per field) or a pinned PairArena (one DMA per micro-batch)."""
 
     def __init__(self, device: torch.device, micro_pairs: int) -> None:
         self.device = device
@@ -133,7 +187,43 @@ class HostStagedRunner:
                 self.h2d_bytes += src[k].numel() * src[k].element_size()
             self.ready[slot].record(self.copy_stream)
 
-    def run(self, host: Dict[str, Tensor], metric: AverageEndPointError) -> float:
+    def _stage_arena(self, slot: int, host: PairArena, lo: int, hi: int) -> None:
+        cur = self.slots[slot]
+        if not isinstance(cur, PairArena) or cur.pairs != hi - lo or cur.shapes != host.shapes:
+            self.slots[slot] = PairArena(hi - lo, host.shapes, device=self.device)
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.freed[slot])       # previous user of this slot has finished
+            self.slots[slot].buf.copy_(host.buf[lo:hi], non_blocking=True)   # whole rows: one contiguous DMA
+            self.h2d_bytes += (hi - lo) * host.pair_floats * 4      # what the DMA moves (payload + <= 2 KB of alignment padding per pair)
+            self.ready[slot].record(self.copy_stream)
+
+    def _run_arena(self, host: PairArena, metric: AverageEndPointError) -> float:
+        if host.buf.is_cuda or not host.buf.is_pinned():
+            raise RuntimeError("HostStagedRunner: the arena must live in pinned host memory")
+        pairs = host.pairs
+        chunks = [(lo, min(lo + self.micro, pairs)) for lo in range(0, pairs, self.micro)]
+        cur = torch.cuda.current_stream(self.device)
+        self._stage_arena(0, host, *chunks[0])
+        for i, _ in enumerate(chunks):
+            slot = i & 1
+            if i + 1 < len(chunks):
+                self._stage_arena(slot ^ 1, host, *chunks[i + 1])
+            cur.wait_event(self.ready[slot])
+            arena = self.slots[slot]
+            dev = {k: arena[k] for k in FIELDS}                 # views; contiguous per field when the micro-batch is 1 pair
+            b, _, h, w = dev["fmap1"].shape
+            if self.lookup_out is None or self.lookup_out.shape[0] != b or self.lookup_out.shape[2:] != (h, w):
+                self.lookup_out = torch.empty((b, 324, h, w), dtype=torch.float32, device=self.device)
+            hot_path(dev, metric, lookup_out=self.lookup_out)
+            self.freed[slot].record(cur)
+        metric.sync()
+        state = metric._acc.cpu()                               # device -> host read of the step's result
+        self.d2h_bytes += state.numel() * state.element_size()
+        return float(state[0] / state[1])
+
+    def run(self, host, metric: AverageEndPointError) -> float:
+        if isinstance(host, PairArena):
+            return self._run_arena(host, metric)
         for k in FIELDS:
             if host[k].is_cuda or not host[k].is_pinned():
                 raise RuntimeError(f"HostStagedRunner: {k} must be a pinned host tensor")
