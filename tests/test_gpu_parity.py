@@ -513,6 +513,13 @@ def test_host_staged_runner_arena_matches_dict():
             got = runner.run(src, AverageEndPointError())
             assert abs(got - want) <= 1e-6 * abs(want), (micro, type(src).__name__)
             assert runner.h2d_bytes >= sum(batch[k].numel() * 4 for k in FIELDS) and runner.d2h_bytes == 16
+        # cross-step prefetch: three steps, the next step's first micro-batch staged during the current one
+        runner = HostStagedRunner(torch.device("cuda", 0), micro)
+        other = PairArena(pairs, PairArena.shapes_of(batch), pin=True).fill(batch)
+        for nxt in (arena, other, None):                       # same arena, a different arena, none
+            got = runner.run(arena if nxt is not other else arena, AverageEndPointError(), prefetch=nxt)
+            assert abs(got - want) <= 1e-6 * abs(want), (micro, "prefetch")
+        assert abs(runner.run(other, AverageEndPointError()) - want) <= 1e-6 * abs(want)   # a stale prefetch is ignored
 
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])

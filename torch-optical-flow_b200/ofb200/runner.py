@@ -167,6 +167,8 @@ class HostStagedRunner:
         self.lookup_out: Optional[Tensor] = None
         self.h2d_bytes = 0
         self.d2h_bytes = 0
+        self._slot = 0                  # slot the next step's first micro-batch goes to
+        self._prefetched = None         # (arena, (lo, hi)) already staged into that slot
 
     def _slice(self, host: Dict[str, Tensor], lo: int, hi: int) -> Dict[str, Tensor]:
         return {k: (host[k][:, lo:hi] if k == "coords" else host[k][lo:hi]) for k in FIELDS}
@@ -197,17 +199,28 @@ class HostStagedRunner:
             self.h2d_bytes += (hi - lo) * host.pair_floats * 4      # what the DMA moves (payload + <= 2 KB of alignment padding per pair)
             self.ready[slot].record(self.copy_stream)
 
-    def _run_arena(self, host: PairArena, metric: AverageEndPointError) -> float:
+    def _run_arena(self, host: PairArena, metric: AverageEndPointError, prefetch: Optional[PairArena]) -> float:
         if host.buf.is_cuda or not host.buf.is_pinned():
             raise RuntimeError("HostStagedRunner: the arena must live in pinned host memory")
         pairs = host.pairs
         chunks = [(lo, min(lo + self.micro, pairs)) for lo in range(0, pairs, self.micro)]
         cur = torch.cuda.current_stream(self.device)
-        self._stage_arena(0, host, *chunks[0])
+        first = self._slot
+        if self._prefetched is not None and self._prefetched[0] is host and self._prefetched[1] == chunks[0]:
+            pass                                                # the previous call already staged this micro-batch
+        else:
+            self._stage_arena(first, host, *chunks[0])
+        self._prefetched = None
         for i, _ in enumerate(chunks):
-            slot = i & 1
+            slot = (first + i) & 1
             if i + 1 < len(chunks):
                 self._stage_arena(slot ^ 1, host, *chunks[i + 1])
+            elif prefetch is not None:
+                # the next step's first micro-batch goes out while this step's last one computes, so the copy
+                # engine never idles across the per-step read-back of the metric
+                nxt = (0, min(self.micro, prefetch.pairs))
+                self._stage_arena(slot ^ 1, prefetch, *nxt)
+                self._prefetched = (prefetch, nxt)
             cur.wait_event(self.ready[slot])
             arena = self.slots[slot]
             dev = {k: arena[k] for k in FIELDS}                 # views; contiguous per field when the micro-batch is 1 pair
@@ -216,14 +229,19 @@ class HostStagedRunner:
                 self.lookup_out = torch.empty((b, 324, h, w), dtype=torch.float32, device=self.device)
             hot_path(dev, metric, lookup_out=self.lookup_out)
             self.freed[slot].record(cur)
+        self._slot = (first + len(chunks)) & 1
         metric.sync()
         state = metric._acc.cpu()                               # device -> host read of the step's result
         self.d2h_bytes += state.numel() * state.element_size()
         return float(state[0] / state[1])
 
-    def run(self, host, metric: AverageEndPointError) -> float:
+    def run(self, host, metric: AverageEndPointError, prefetch: Optional[PairArena] = None) -> float:
+        """One step over `host`.  `prefetch` (arena path): the arena of the NEXT step; its first micro-batch is
+        staged while this step finishes and the next `run(prefetch, ...)` picks it up."""
         if isinstance(host, PairArena):
-            return self._run_arena(host, metric)
+            return self._run_arena(host, metric, prefetch)
+        self._prefetched = None
+        self._slot = 0
         for k in FIELDS:
             if host[k].is_cuda or not host[k].is_pinned():
                 raise RuntimeError(f"HostStagedRunner: {k} must be a pinned host tensor")
