@@ -54,7 +54,7 @@ __device__ __forceinline__ Tap make_tap(float cen, int t, int radius, int size) 
 }
 
 template <int R>
-__global__ void __launch_bounds__(128) lookup_bwd_kernel(const BwdParams P, const float* __restrict__ coords,
+__global__ void __launch_bounds__(128) lookup_bwd_kernel(const __grid_constant__ BwdParams P, const float* __restrict__ coords,
                                                          const float* __restrict__ d_out) {
     constexpr int D = 2 * R + 1, DD = D * D;
     const long long HW = (long long)P.h * P.w, Q = (long long)P.B * HW;
