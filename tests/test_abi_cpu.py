@@ -121,3 +121,30 @@ def test_pair_arena_layout_cpu():
         want = batch[k][:, 1:3] if k == "coords" else batch[k][1:3]
         assert torch.equal(sub, want)
     assert arena.payload_bytes_per_pair == 4 * sum(batch[k].numel() for k in FIELDS) // pairs
+
+
+def test_input_padder_known_answers_cpu():
+    """model.InputPadder (caller-side torch glue; behaviour of reference methods/raft/model/utils.py:38-61): the
+    paddings SURVEY.md section 8 quotes -- Sintel 436 -> 440 centred, KITTI 375 x 1242 -> 376 x 1248 with the extra
+    row at the bottom -- replicate values, and unpad inverts pad."""
+    import torch
+
+    from model.utils import InputPadder, coords_grid
+
+    x = torch.arange(436 * 1024, dtype=torch.float32).view(1, 1, 436, 1024)
+    p = InputPadder(x.shape)
+    (y,) = p.pad(x)
+    assert y.shape == (1, 1, 440, 1024) and torch.equal(y[0, 0, 0], x[0, 0, 0]) and torch.equal(y[0, 0, 2], x[0, 0, 0])
+    assert torch.equal(y[0, 0, -1], x[0, 0, -1]) and torch.equal(p.unpad(y), x)
+    k = torch.rand(2, 3, 375, 1242)
+    pk = InputPadder(k.shape, mode="kitti")
+    a, b = pk.pad(k, 2 * k)
+    assert a.shape == (2, 3, 376, 1248) and torch.equal(a[:, :, 0, 3:-3], k[:, :, 0]) and torch.equal(a[:, :, -1, 3:-3], k[:, :, -1])
+    assert torch.equal(a[:, :, :, 0], a[:, :, :, 3]) and torch.equal(pk.unpad(b), 2 * k)
+    odd = torch.rand(1, 1, 7, 9)
+    po = InputPadder(odd.shape)                      # 1 extra row -> bottom, 7 extra columns -> 3 left, 4 right
+    (z,) = po.pad(odd)
+    assert z.shape == (1, 1, 8, 16) and torch.equal(z[..., :7, 3:12], odd) and torch.equal(po.unpad(z), odd)
+    g = coords_grid(2, 3, 4)
+    assert g.shape == (2, 2, 3, 4) and g.dtype == torch.float32
+    assert torch.equal(g[1, 0, 2], torch.arange(4.0)) and torch.equal(g[0, 1, :, 1], torch.arange(3.0))

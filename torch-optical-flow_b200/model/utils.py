@@ -10,26 +10,32 @@ from optical_flow.operator.operator import _check_f32, _resize_raw, _run
 
 
 class InputPadder:
-    """Pads images such that dimensions are divisible by 8 (reference utils.py:38-61).
+    """Replicate-pads images up to the next multiple of 8 in both dimensions and crops results back (behaviour of
+    reference utils.py:38-61).  Caller-side helper, not on the accelerated path.
 
-    Caller-side helper, not on the accelerated path: plain replicate padding."""
+    mode "sintel": the extra rows / columns are split evenly (the odd one goes to the bottom / right);
+    any other mode: columns split evenly, all extra rows at the bottom (KITTI)."""
+
+    MULTIPLE = 8
 
     def __init__(self, dims: Sequence[int], mode: str = "sintel") -> None:
-        self.ht, self.wd = dims[-2:]
-        pad_ht = (((self.ht // 8) + 1) * 8 - self.ht) % 8
-        pad_wd = (((self.wd // 8) + 1) * 8 - self.wd) % 8
+        height, width = int(dims[-2]), int(dims[-1])
+        extra_h = -height % self.MULTIPLE
+        extra_w = -width % self.MULTIPLE
+        self.left, self.right = extra_w // 2, extra_w - extra_w // 2
         if mode == "sintel":
-            self._pad = [pad_wd // 2, pad_wd - pad_wd // 2, pad_ht // 2, pad_ht - pad_ht // 2]
+            self.top, self.bottom = extra_h // 2, extra_h - extra_h // 2
         else:
-            self._pad = [pad_wd // 2, pad_wd - pad_wd // 2, 0, pad_ht]
+            self.top, self.bottom = 0, extra_h
+        self.ht, self.wd = height, width
 
     def pad(self, *inputs: Tensor) -> List[Tensor]:
-        return [F.pad(x, self._pad, mode="replicate") for x in inputs]
+        amounts = (self.left, self.right, self.top, self.bottom)
+        return [F.pad(image, amounts, mode="replicate") for image in inputs]
 
     def unpad(self, x: Tensor) -> Tensor:
-        ht, wd = x.shape[-2:]
-        c = [self._pad[2], ht - self._pad[3], self._pad[0], wd - self._pad[1]]
-        return x[..., c[0] : c[1], c[2] : c[3]]
+        rows, cols = x.shape[-2] - self.top - self.bottom, x.shape[-1] - self.left - self.right
+        return x.narrow(-2, self.top, rows).narrow(-1, self.left, cols)
 
 
 def bilinear_sampler(
@@ -60,8 +66,8 @@ def bilinear_sampler(
 def coords_grid(batch: int, ht: int, wd: int) -> Tensor:
     """(batch, 2, ht, wd) fp32 grid, channel 0 = x (column), channel 1 = y (row) (reference utils.py:83-86)."""
     ys, xs = torch.meshgrid(torch.arange(ht), torch.arange(wd), indexing="ij")
-    coords = torch.stack((xs, ys), dim=0).float()
-    return coords[None].repeat(batch, 1, 1, 1)
+    grid = torch.stack((xs, ys), dim=0).to(torch.float32)
+    return grid.unsqueeze(0).expand(batch, -1, -1, -1).contiguous()
 
 
 def upflow8(flow: Tensor, mode: str = "bilinear") -> Tensor:
@@ -69,5 +75,5 @@ def upflow8(flow: Tensor, mode: str = "bilinear") -> Tensor:
     if mode != "bilinear":
         raise NotImplementedError(f"upflow8: mode={mode!r} has no B200 kernel (bilinear only)")
     _check_f32(flow)
-    new_size = (8 * flow.shape[2], 8 * flow.shape[3])
-    return _resize_raw(flow, new_size, True, 8.0, 8.0, "upflow8")
+    h, w = flow.shape[-2:]
+    return _resize_raw(flow, (8 * h, 8 * w), True, 8.0, 8.0, "upflow8")

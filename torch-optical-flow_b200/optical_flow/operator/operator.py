@@ -195,33 +195,39 @@ def resize(
     if mode != "bilinear":
         raise NotImplementedError(f"resize: mode={mode!r} has no B200 kernel (bilinear only)")
     _check_f32(flow)
-    b, _, h, w = flow.shape
-    if scale_factor:
-        size = (round(h * scale_factor), round(w * scale_factor))
-    sy = size[0] / h
-    sx = size[1] / w
-    return _resize_raw(flow, size, False, sx, sy, "resize")
+    in_h, in_w = flow.shape[-2:]
+    if scale_factor:                                     # Python's round: banker's rounding, as the reference (:109)
+        size = (round(in_h * scale_factor), round(in_w * scale_factor))
+    out_h, out_w = int(size[0]), int(size[1])
+    # the flow vectors are measured in pixels of the new grid: x scales with the width ratio, y with the height ratio
+    return _resize_raw(flow, (out_h, out_w), False, out_w / in_w, out_h / in_h, "resize")
+
+
+def _half_extent(flow: Tensor) -> Tuple[float, float]:
+    """(W-1)/2, (H-1)/2 with the reference's guard for single-pixel dimensions (operator.py:129,145)."""
+    rows, cols = flow.shape[-2:]
+    return max(cols - 1, 1) / 2, max(rows - 1, 1) / 2
 
 
 def normalize(flow: Tensor) -> Tensor:
     """Pixel units -> normalised [-1, 1] units (reference operator.py:117-130)."""
     assert flow.size(1) == 2
-    h, w = flow.shape[-2:]
-    return scale(flow, (2.0 / max(w - 1, 1), 2.0 / max(h - 1, 1)))
+    half_w, half_h = _half_extent(flow)
+    return scale(flow, (1.0 / half_w, 1.0 / half_h))
 
 
 def denormalize(flow: Tensor) -> Tensor:
     """Normalised units -> pixel units (reference operator.py:133-146)."""
     assert flow.size(1) == 2
-    h, w = flow.shape[-2:]
-    return scale(flow, (max(w - 1, 1) / 2, max(h - 1, 1) / 2))
+    return scale(flow, _half_extent(flow))
 
 
 def integrate(*flows: Tensor) -> Tensor:
-    """Integrates a sequence of flow maps into one (reference operator.py:149-165)."""
+    """Integrates a sequence of flow maps into one (reference operator.py:149-165): a right fold,
+    total_k = flow_k + warp(total_{k+1}, flow_k), starting from the last flow."""
     assert len(flows) >= 2
-    total = flows[-1]
-    for flow in reversed(flows[:-1]):
-        assert flow.shape == total.shape, "All flows must have the same size."
-        total = flow + warp(total, flow)
-    return total
+    assert all(f.shape == flows[0].shape for f in flows), "integrate: the flows differ in shape"
+    accumulated = flows[-1]
+    for step in range(len(flows) - 2, -1, -1):
+        accumulated = flows[step] + warp(accumulated, flows[step])
+    return accumulated
