@@ -15,10 +15,9 @@ class OutlierRatio:
     """Ratio of pixels whose end-point error exceeds `abs_threshold` *and* whose relative error exceeds
     `rel_threshold` (reference f1.py:10-51).
 
-    Args:
-        dim: the dimension along which to compute the end-point-error (only 1 is supported)
-        abs_threshold: the threshold of absolute error above which a pixel is considered an outlier
-        rel_threshold: the threshold of relative error above which a pixel is considered an outlier
+    dim            flow-component dimension of `pred` / `target` (only 1 is supported by the kernel)
+    abs_threshold  a pixel can only be an outlier when its end-point error is above this many pixels ...
+    rel_threshold  ... and above this fraction of the ground-truth flow magnitude (KITTI: 3 px and 5 %)
     """
 
     def __init__(self, dim: int = 1, abs_threshold: float = 3.0, rel_threshold: float = 0.05) -> None:
