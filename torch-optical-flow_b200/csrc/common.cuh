@@ -23,15 +23,24 @@ extern int64_t g_ofb_launches;  // api.cu
         if (e__ != cudaSuccess) return (int)e__;   \
     } while (0)
 
+// Function attributes and the SM count belong to a device: cache them per device, so a process that drives several
+// GPUs (not the one-process-per-GPU model of the bench, but legal for a library) configures each of them.
+constexpr int OFB_MAX_DEVICES = 64;
+static inline int ofb_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < OFB_MAX_DEVICES) ? dev : 0;
+}
+
 static inline int ofb_num_sms() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
+    static int sms[OFB_MAX_DEVICES] = {0};
+    const int dev = ofb_device();
+    if (!sms[dev]) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        sms[dev] = n > 0 ? n : 148;
     }
-    return sms;
+    return sms[dev];
 }
 
 namespace ofb {

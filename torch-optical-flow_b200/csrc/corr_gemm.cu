@@ -674,11 +674,12 @@ bool encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims
 
 template <int CG, bool PROF, int LAY>
 int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& P, int grid, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[OFB_MAX_DEVICES] = {false};
+    const int dev = ofb_device();
+    if (!configured[dev]) {
         OFB_CUDA(cudaFuncSetAttribute(corr_pyramid_kernel<CG, PROF, LAY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Ring<CG, LAY>::SMEM_ALLOC));
-        configured = true;
+        configured[dev] = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);

@@ -481,9 +481,14 @@ OFB_API int ofb_corr_lookup(const ofb_pyramid* pyr, const float* coords, float* 
         if (!gr) {                                         // than one group for the whole window); OFB_LOOKUP_GR=16 for A/B
             const char* e = getenv("OFB_LOOKUP_GR");
             gr = (e && atoi(e) == 16) ? 16 : 3;
+        }
+        static bool configured[OFB_MAX_DEVICES] = {false};
+        const int dev = ofb_device();
+        if (!configured[dev]) {
             OFB_CUDA(cudaFuncSetAttribute(lookup_tile_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 11 * 128 * 40));
             OFB_CUDA(cudaFuncSetAttribute(lookup_tile_kernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 11 * 128 * 40));
             OFB_CUDA(cudaFuncSetAttribute(lookup_tile_kernel<3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 128 * 40));
+            configured[dev] = true;
         }
         if (radius == 4 && gr == 3) lookup_tile_kernel<4, 3><<<(int)blocks, threads, wsm, st>>>(P, coords, out, idx_or_null, valid_or_null);
         else if (radius == 4) lookup_tile_kernel<4, 16><<<(int)blocks, threads, wsm, st>>>(P, coords, out, idx_or_null, valid_or_null);

@@ -416,11 +416,12 @@ int launch_staged(const float* frame, const float* flow, float* out, uint8_t* va
                   FlowMul fm, cudaStream_t st) {
     const int cg = C < CG_MAX ? C : CG_MAX;
     const size_t smem = (size_t)cg * WIN_H * WIN_W * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[OFB_MAX_DEVICES] = {false};
+    const int dev = ofb_device();
+    if (!configured[dev]) {
         OFB_CUDA(cudaFuncSetAttribute(warp_staged_kernel<PAD, AC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(CG_MAX * WIN_H * WIN_W * sizeof(float))));
-        configured = true;
+        configured[dev] = true;
     }
     const int vec4 = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(frame) & 15) == 0);
     dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, B);

@@ -254,11 +254,12 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 template <int PAD, bool AC>
 int launch(const CUtensorMap& map, const float* frame, const float* flow, float* out, uint8_t* valid, int B, int C,
            int H, int W, FlowMul2 fm, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[OFB_MAX_DEVICES] = {false};
+    const int dev = ofb_device();
+    if (!configured[dev]) {
         OFB_CUDA(cudaFuncSetAttribute(warp_tma_kernel<PAD, AC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       STAGES * CGRP * PLANE_BYTES));
-        configured = true;
+        configured[dev] = true;
     }
     const int cg = C < CGRP ? C : CGRP;
     const size_t smem = (size_t)STAGES * cg * PLANE_BYTES;
