@@ -148,3 +148,38 @@ def test_input_padder_known_answers_cpu():
     g = coords_grid(2, 3, 4)
     assert g.shape == (2, 2, 3, 4) and g.dtype == torch.float32
     assert torch.equal(g[1, 0, 2], torch.arange(4.0)) and torch.equal(g[0, 1, :, 1], torch.arange(3.0))
+
+
+def test_host_side_argument_errors_cpu():
+    """Argument checks of the Python surface that fire before any device work (so they are testable without a GPU),
+    with the reference's exception types: shape preconditions are bare asserts (operator.py:74,77,128,144,160)."""
+    import pytest
+    import torch
+
+    from model import sequence_loss
+    from optical_flow import denormalize, integrate, normalize, resize, scale, warp
+
+    gt, valid = torch.zeros(1, 2, 4, 4), torch.ones(1, 4, 4)
+    with pytest.raises(ValueError):
+        sequence_loss([], gt, valid)
+    with pytest.raises(NotImplementedError):
+        sequence_loss([gt] * 25, gt, valid)
+    with pytest.raises(RuntimeError):
+        sequence_loss([torch.zeros(1, 2, 4, 5)], gt, valid)
+    for fn in (normalize, denormalize, lambda f: scale(f, 2.0), lambda f: resize(f, size=(2, 2))):
+        with pytest.raises(AssertionError):
+            fn(torch.zeros(1, 3, 4, 4))
+    with pytest.raises(AssertionError):
+        scale(gt, (1.0, 2.0, 3.0))
+    with pytest.raises(AssertionError):
+        integrate(gt)
+    with pytest.raises(AssertionError):
+        integrate(gt, torch.zeros(1, 2, 4, 5))
+    with pytest.raises(NotImplementedError):
+        warp(torch.zeros(1, 3, 4, 4), gt, mode="bicubic")
+    with pytest.raises(ValueError):
+        warp(torch.zeros(1, 3, 4, 4), gt, padding_mode="wrap")
+    with pytest.raises(NotImplementedError):
+        resize(gt, size=(2, 2), mode="nearest")
+    with pytest.raises(NotImplementedError):
+        warp(torch.zeros(1, 3, 4, 4, dtype=torch.float64), gt.double())
