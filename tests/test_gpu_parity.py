@@ -486,6 +486,39 @@ def test_corr_block_backward(golden):
     assert g2.grad is not None and bool(torch.isfinite(g2.grad).all())
 
 
+def test_corr_block_4k_indexing():
+    """2160 x 3840 frames (270 x 480 features): level 0 of ONE pair holds 1.68e10 elements (33.6 GB in bf16), past
+    2^32 -- every offset in the builder and the lookup has to be 64-bit.  Sampled queries from the start, the
+    middle and the very end of the volume are checked against direct dot products."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 70e9:
+        pytest.skip("needs ~50 GB of free device memory")
+    from model import CorrBlock
+
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    c, h, w = 64, 270, 480
+    n = h * w
+    f1 = torch.randn((1, c, h, w), device="cuda", generator=gen)
+    f2 = torch.randn((1, c, h, w), device="cuda", generator=gen)
+    blk = CorrBlock(f1, f2, num_levels=4, radius=4)
+    ys, xs = torch.meshgrid(torch.arange(h, device="cuda"), torch.arange(w, device="cuda"), indexing="ij")
+    coords = torch.stack((xs, ys), 0).float()[None].contiguous()            # integer coordinates: taps are exact samples
+    out = blk(coords)                                                       # (1, 324, h, w)
+    assert bool(torch.isfinite(out).all())
+    a = (f1[0].reshape(c, n) / 8.0).to(torch.bfloat16).float()              # operands as the builder rounds them (1/sqrt(64))
+    b2 = f2[0].reshape(c, n).to(torch.bfloat16).float()
+    for q in (0, 1, n // 2 + 7, n - w - 3, n - 1):
+        qy, qx = divmod(q, w)
+        row = (a[:, q] @ b2).view(h, w)                                      # level-0 slice of query q, fp32
+        for i, j in ((4, 4), (0, 0), (8, 8), (2, 7)):                        # channel i*9 + j samples (x + i - 4, y + j - 4)
+            x, y = qx + i - 4, qy + j - 4
+            want = float(row[y, x]) if 0 <= x < w and 0 <= y < h else 0.0
+            got = float(out[0, i * 9 + j, qy, qx])
+            assert abs(got - want) <= 2e-2 * max(1.0, abs(want)), (q, i, j, got, want)
+    del blk, out
+    torch.cuda.empty_cache()
+
+
 def test_host_staged_runner_arena_matches_dict():
     """HostStagedRunner: a pinned pair-major arena (one DMA per micro-batch) gives the same EPE as the per-field
     staging of a dict of pinned tensors and as the device-resident pass, for micro-batches of 1 and 2 pairs."""
