@@ -486,6 +486,34 @@ def test_corr_block_backward(golden):
     assert g2.grad is not None and bool(torch.isfinite(g2.grad).all())
 
 
+def test_empty_batches():
+    """Zero-size inputs: every op returns an empty tensor of the right shape (as the ATen ops behind the reference
+    do) instead of tripping over the null data pointer of an empty tensor; metrics stay untouched."""
+    from model import CorrBlock, bilinear_sampler, upflow8, upsample_flow
+    from optical_flow import normalize, resize, warp
+    from optical_flow.metrics import AverageEndPointError, OutlierRatio
+
+    z = lambda *s: torch.zeros(s, device="cuda")
+    out, mask = warp(z(0, 3, 8, 8), z(0, 2, 8, 8), return_mask=True)
+    assert out.shape == (0, 3, 8, 8) and mask.shape == (0, 8, 8)
+    assert warp(z(2, 0, 8, 8), z(2, 2, 8, 8)).shape == (2, 0, 8, 8)
+    assert normalize(z(0, 2, 4, 4)).shape == (0, 2, 4, 4)
+    assert resize(z(0, 2, 4, 4), size=(8, 6)).shape == (0, 2, 8, 6)
+    assert upflow8(z(0, 2, 3, 3)).shape == (0, 2, 24, 24)
+    assert upsample_flow(z(0, 2, 3, 3), z(0, 576, 3, 3)).shape == (0, 2, 24, 24)
+    assert bilinear_sampler(z(0, 1, 5, 5), z(0, 3, 3, 2)).shape == (0, 1, 3, 3)
+    blk = CorrBlock(z(0, 64, 8, 8), z(0, 64, 8, 8), num_levels=2, radius=4)
+    assert blk(z(0, 2, 8, 8)).shape == (0, 2 * 81, 8, 8)
+    for m in (AverageEndPointError(), OutlierRatio()):
+        m.update(z(0, 2, 4, 4), z(0, 2, 4, 4))
+        m.update(torch.ones(1, 2, 4, 4, device="cuda"), z(1, 2, 4, 4))
+        assert int(m.total) == 16
+    # gradients through an empty warp are empty too
+    fr = z(0, 3, 8, 8).requires_grad_(True)
+    warp(fr, z(0, 2, 8, 8)).sum().backward()
+    assert fr.grad.shape == (0, 3, 8, 8)
+
+
 def test_corr_block_4k_indexing():
     """2160 x 3840 frames (270 x 480 features): level 0 of ONE pair holds 1.68e10 elements (33.6 GB in bf16), past
     2^32 -- every offset in the builder and the lookup has to be 64-bit.  Sampled queries from the start, the

@@ -788,6 +788,7 @@ int run_gemm(const void* f1_km, const void* f2_km, const ofb_pyramid* pyr, int l
 
 int corr_pyramid_impl(const void* f1_km, const void* f2_km, const void* f2q_km, const ofb_pyramid* pyr, int B, int C, int h,
                       int w, float scale, int cta_group, unsigned long long* prof, void* stream) {
+    if (B == 0) return OFB_OK;   // nothing to do: empty tensors have no storage, their pointers may be null
     if (!f1_km || !f2_km || !pyr || B < 0 || C <= 0 || h <= 0 || w <= 0) return OFB_EINVAL;
     if (cta_group < 0 || cta_group > 2) return OFB_EINVAL;
     if (pyr->levels < 1 || pyr->levels > OFB_MAX_LEVELS) return OFB_EINVAL;

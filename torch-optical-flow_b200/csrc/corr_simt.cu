@@ -163,6 +163,7 @@ int build_simt(const float* f1, const float* f2, const ofb_pyramid* pyr, int B, 
 
 OFB_API int ofb_corr_prep_bf16(const float* fmap_nchw, void* out_km_bf16, int B, int C, int h, int w, int pool,
                                float scale, void* stream) {
+    if (B == 0) return OFB_OK;   // nothing to do: empty tensors have no storage, their pointers may be null
     if (!fmap_nchw || !out_km_bf16 || B < 0 || C <= 0 || h <= 0 || w <= 0) return OFB_EINVAL;
     if (pool != 1 && pool != 4) return OFB_EINVAL;
     if (C & 1) return OFB_EUNSUPPORTED;
@@ -204,6 +205,7 @@ OFB_API int ofb_pyramid_layout(int h, int w, int levels, int mode, ofb_pyramid* 
 
 OFB_API int ofb_corr_pyramid_simt_f32(const float* fmap1, const float* fmap2, const ofb_pyramid* pyr, int B, int C,
                                       int h, int w, float scale, void* stream) {
+    if (B == 0) return OFB_OK;   // nothing to do: empty tensors have no storage, their pointers may be null
     if (!fmap1 || !fmap2 || !pyr || B < 0 || C <= 0 || h <= 0 || w <= 0) return OFB_EINVAL;
     if (pyr->levels < 1 || pyr->levels > OFB_MAX_LEVELS) return OFB_EINVAL;
     if (pyr->layout != OFB_LAYOUT_ROWS) return OFB_EUNSUPPORTED;      // the CUDA-core builder writes rows

@@ -216,6 +216,7 @@ namespace {
 template <int MODE>
 int launch_reduce(const float* pred, const float* target, const float* valid_or_null, double* acc, int B, int H, int W,
                   float abs_thr, float rel_thr, void* stream) {
+    if (B == 0 || H == 0 || W == 0) return OFB_OK;   // nothing to do: empty tensors have no storage, their pointers may be null
     if (!pred || !target || !acc || B < 0 || H < 0 || W < 0) return OFB_EINVAL;
     const int64_t HW = (int64_t)H * W;
     if ((int64_t)B * HW == 0) return OFB_OK;
@@ -244,6 +245,7 @@ OFB_API int ofb_outlier_reduce_f32(const float* pred, const float* target, const
 }
 
 OFB_API int ofb_epe_map_f32(const float* pred, const float* target, float* out, int B, int H, int W, void* stream) {
+    if (B == 0 || H == 0 || W == 0) return OFB_OK;   // nothing to do: empty tensors have no storage, their pointers may be null
     if (!pred || !target || !out || B < 0 || H < 0 || W < 0) return OFB_EINVAL;
     const int64_t HW = (int64_t)H * W;
     if ((int64_t)B * HW == 0) return OFB_OK;
@@ -257,6 +259,7 @@ OFB_API int ofb_epe_map_f32(const float* pred, const float* target, float* out, 
 
 OFB_API int ofb_sequence_loss_f32(const float* const* preds, int n_predictions, const float* flow_gt, const float* valid,
                                   double* acc, int B, int H, int W, double gamma, float max_flow, void* stream) {
+    if (n_predictions >= 1 && (B == 0 || H == 0 || W == 0)) return OFB_OK;   // nothing to do: empty tensors have no storage, their pointers may be null
     if (!preds || !flow_gt || !valid || !acc || B < 0 || H < 0 || W < 0 || n_predictions < 1) return OFB_EINVAL;
     if (n_predictions > MAX_PREDS) return OFB_EUNSUPPORTED;
     const int64_t HW = (int64_t)H * W;

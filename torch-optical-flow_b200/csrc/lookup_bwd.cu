@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(128) lookup_bwd_kernel(const __grid_constant__
 
 OFB_API int ofb_corr_lookup_backward_f32(const ofb_pyramid* d_pyr, const float* coords, const float* d_out, int B, int h,
                                          int w, int radius, void* stream) {
+    if (B == 0) return OFB_OK;   // nothing to do: empty tensors have no storage, their pointers may be null
     if (!d_pyr || !coords || !d_out || B < 0 || h <= 0 || w <= 0) return OFB_EINVAL;
     if (d_pyr->levels < 1 || d_pyr->levels > OFB_MAX_LEVELS) return OFB_EINVAL;
     if (d_pyr->dtype != OFB_DTYPE_F32 || d_pyr->layout != OFB_LAYOUT_ROWS) return OFB_EUNSUPPORTED;

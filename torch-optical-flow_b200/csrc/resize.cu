@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(256) scale_flow_kernel(const float* __restrict
 
 OFB_API int ofb_resize_bilinear_f32(const float* in, float* out, int N, int C, int H, int W, int Ho, int Wo,
                                     int align_corners, float mul_x, float mul_y, void* stream) {
+    if (N == 0 || C == 0 || Ho == 0 || Wo == 0) return OFB_OK;   // nothing to do: empty tensors have no storage, their pointers may be null
     if (!in || !out || N < 0 || C < 0 || H <= 0 || W <= 0 || Ho < 0 || Wo < 0) return OFB_EINVAL;
     if ((C & 1) && (mul_x != mul_y)) return OFB_EINVAL;   // per-axis factors need (x,y) channel pairs
     const size_t total = (size_t)N * C * Ho * ((Wo + 3) / 4);
@@ -127,6 +128,7 @@ OFB_API int ofb_resize_bilinear_f32(const float* in, float* out, int N, int C, i
 
 OFB_API int ofb_resize_bilinear_backward_f32(const float* d_out, float* d_in, int N, int C, int H, int W, int Ho, int Wo,
                                              int align_corners, float mul_x, float mul_y, void* stream) {
+    if (N == 0 || C == 0 || Ho == 0 || Wo == 0) return OFB_OK;   // nothing to do: empty tensors have no storage, their pointers may be null
     if (!d_out || !d_in || N < 0 || C < 0 || H <= 0 || W <= 0 || Ho < 0 || Wo < 0) return OFB_EINVAL;
     if ((C & 1) && (mul_x != mul_y)) return OFB_EINVAL;
     const size_t total = (size_t)N * C * Ho * Wo;
@@ -149,6 +151,7 @@ OFB_API int ofb_resize_bilinear_backward_f32(const float* d_out, float* d_in, in
 }
 
 OFB_API int ofb_scale_flow_f32(const float* flow, float* out, int B, int64_t HW, float fx, float fy, void* stream) {
+    if (B == 0 || HW == 0) return OFB_OK;   // nothing to do: empty tensors have no storage, their pointers may be null
     if (!flow || !out || B < 0 || HW < 0) return OFB_EINVAL;
     const int64_t total = (int64_t)B * 2 * HW;
     if (total == 0) return OFB_OK;

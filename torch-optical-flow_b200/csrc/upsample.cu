@@ -174,6 +174,7 @@ __global__ void __launch_bounds__(NT) convex_upsample_bwd_kernel(const float* __
 }  // namespace
 
 OFB_API int ofb_convex_upsample_f32(const float* flow, const float* mask, float* out, int N, int h, int w, void* stream) {
+    if (N == 0 || h == 0 || w == 0) return OFB_OK;   // nothing to do: empty tensors have no storage, their pointers may be null
     if (!flow || !mask || !out || N < 0 || h < 0 || w < 0) return OFB_EINVAL;
     if ((size_t)N * h * w == 0) return OFB_OK;
     if (N > 65535) return OFB_EUNSUPPORTED;
@@ -187,6 +188,7 @@ OFB_API int ofb_convex_upsample_f32(const float* flow, const float* mask, float*
 OFB_API int ofb_convex_upsample_backward_f32(const float* flow, const float* mask, const float* d_out,
                                              float* d_flow_or_null, float* d_mask_or_null, int N, int h, int w,
                                              void* stream) {
+    if (N == 0 || h == 0 || w == 0) return OFB_OK;   // nothing to do: empty tensors have no storage, their pointers may be null
     if (!flow || !mask || !d_out || N < 0 || h < 0 || w < 0) return OFB_EINVAL;
     if ((size_t)N * h * w == 0 || (!d_flow_or_null && !d_mask_or_null)) return OFB_OK;
     if (N > 65535) return OFB_EUNSUPPORTED;

@@ -471,6 +471,7 @@ int ofb_warp_tma_launch(const float* frame, const float* flow, float* out, uint8
 OFB_API int ofb_warp_f32(const float* frame, const float* flow, float* out, uint8_t* valid_or_null, int B, int C, int H,
                          int W, int mode, int padding_mode, int align_corners, int channels_last, int variant,
                          float flow_mul_x, float flow_mul_y, void* stream) {
+    if (B == 0 || C == 0 || H == 0 || W == 0) return OFB_OK;   // nothing to do: empty tensors have no storage, their pointers may be null
     if (!frame || !flow || !out || B < 0 || C < 0 || H < 0 || W < 0) return OFB_EINVAL;
     if (mode != OFB_MODE_BILINEAR && mode != OFB_MODE_NEAREST) return OFB_EINVAL;
     if (padding_mode < 0 || padding_mode > 2 || variant < 0 || variant > 4) return OFB_EINVAL;
@@ -505,6 +506,7 @@ OFB_API int ofb_warp_f32(const float* frame, const float* flow, float* out, uint
 }
 
 OFB_API int ofb_warp_grid_f32(const float* flow_bhw2, float* grid_bhw2, int B, int H, int W, void* stream) {
+    if (B == 0 || H == 0 || W == 0) return OFB_OK;   // nothing to do: empty tensors have no storage, their pointers may be null
     if (!flow_bhw2 || !grid_bhw2 || B < 0 || H < 0 || W < 0) return OFB_EINVAL;
     const size_t total = (size_t)B * H * W;
     if (total == 0) return OFB_OK;

@@ -120,6 +120,7 @@ int launch(const float* frame, const float* flow, const float* d_out, float* d_f
 OFB_API int ofb_warp_backward_f32(const float* frame, const float* flow, const float* d_out, float* d_frame_or_null,
                                   float* d_flow_or_null, int B, int C, int H, int W, int padding_mode, int align_corners,
                                   float flow_mul_x, float flow_mul_y, void* stream) {
+    if (B == 0 || H == 0 || W == 0) return OFB_OK;   // nothing to do: empty tensors have no storage, their pointers may be null
     if (!frame || !flow || !d_out || B < 0 || C < 0 || H < 0 || W < 0) return OFB_EINVAL;
     if (padding_mode < 0 || padding_mode > 2) return OFB_EINVAL;
     if ((size_t)B * H * W == 0 || (!d_frame_or_null && !d_flow_or_null)) return OFB_OK;
