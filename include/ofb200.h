@@ -251,6 +251,21 @@ int ofb_corr_lookup(const ofb_pyramid* pyr_host, const float* coords, float* out
 int ofb_corr_lookup_backward_f32(const ofb_pyramid* d_pyr, const float* coords, const float* d_out,
                                  int B, int h, int w, int radius, void* stream);
 
+/* The two GEMMs behind d CorrBlock / d fmap (autograd through corr.py:45-54,79-87), on the tensor cores:
+ *   D[b] (M x N, fp32, row pitch ldd) = alpha * A[b] (M x K) . B[b]^T (N x K)  (+ D[b] when accumulate != 0)
+ * A, B bf16, K-major (row pitches lda, ldb and batch strides in elements, multiples of 8); N a multiple of 32,
+ * <= 256; all bases 16-byte aligned.  With dP_l the fp32 gradient of pyramid level l:
+ *   d fmap1^T = sum_l dP_l . pool_l(fmap2)        A = bf16(dP_l) (queries x targets),   B = pool_l(fmap2) (C x targets)
+ *   d pool_l(fmap2)^T = dP_l^T . fmap1^T          A = bf16(dP_l)^T (targets x queries), B = fmap1 (C x queries)
+ * ofb_cast_bf16 produces both A operands from the fp32 level in one pass: a bf16 copy (row pitch
+ * pitch_dst >= cols) and / or the bf16 transpose (row pitch pitch_dst_t >= rows); pitches at most the next
+ * multiple of 32, padding zero-filled. */
+int ofb_gemm_nt_bf16(const void* A, const void* B, float* D, int batch, int M, int N, int K,
+                     long long lda, long long ldb, long long ldd, long long strideA, long long strideB,
+                     long long strideD, float alpha, int accumulate, void* stream);
+int ofb_cast_bf16(const float* src, void* dst_or_null, void* dst_t_or_null, int batch, int rows, int cols,
+                  long long pitch_dst, long long pitch_dst_t, void* stream);
+
 /* bilinear_sampler (utils.py:64-80) for arbitrary images: img (N,C,H,W), coords (N,Ho,Wo,2)
  * pixel units -> out (N,C,Ho,Wo) [+ mask (N,Ho,Wo) fp32 0/1]. */
 int ofb_bilinear_sampler_f32(const float* img, const float* coords, float* out, float* mask_or_null,

@@ -434,6 +434,53 @@ def test_outlier_ratio_golden_and_oracle(golden):
     assert float(m._acc[0]) == s and int(m.total) == n
 
 
+def _gemm_nt(a, b, accumulate_into=None, alpha=1.0):
+    """ofb_gemm_nt_bf16 on (batch, M, lda) / (batch, N, ldb) bf16 tensors whose logical K is the last argument."""
+    import ofb200
+    (a_t, k), (b_t, _) = a, b
+    batch, m, lda = a_t.shape
+    n, ldb = b_t.shape[1], b_t.shape[2]
+    d = accumulate_into if accumulate_into is not None else torch.empty((batch, m, n), device="cuda")
+    ofb200.check(ofb200.load().ofb_gemm_nt_bf16(ofb200.ptr(a_t), ofb200.ptr(b_t), ofb200.ptr(d), batch, m, n, k, lda, ldb, n,
+                                                m * lda, n * ldb, m * n, alpha, int(accumulate_into is not None),
+                                                ofb200.stream_ptr()), "ofb_gemm_nt_bf16")
+    return d
+
+
+@pytest.mark.parametrize("batch,m,n,k", [(1, 128, 256, 64), (2, 300, 256, 1000), (1, 7332, 256, 7332), (3, 130, 64, 72),
+                                         (1, 33, 128, 2040), (2, 1, 32, 8)])
+def test_gemm_nt_bf16_and_cast(batch, m, n, k):
+    """The backward GEMM kernel (tcgen05, long K) and the cast / transpose that feeds it, against torch: ragged M and
+    K tails, every N the kernel accepts, accumulation, alpha."""
+    import ofb200
+
+    gen = torch.Generator(device="cuda").manual_seed(m * 7 + k)
+    src = torch.randn((batch, m, k), device="cuda", generator=gen)           # fp32 "gradient level": rows x cols
+    bop = torch.randn((batch, n, k), device="cuda", generator=gen)
+    pk, pm = (k + 7) // 8 * 8, (m + 7) // 8 * 8
+    a16 = torch.full((batch, m, pk), 7.0, dtype=torch.bfloat16, device="cuda")
+    a16_t = torch.full((batch, k, pm), 7.0, dtype=torch.bfloat16, device="cuda")
+    ofb200.check(ofb200.load().ofb_cast_bf16(ofb200.ptr(src), ofb200.ptr(a16), ofb200.ptr(a16_t), batch, m, k, pk, pm,
+                                             ofb200.stream_ptr()), "ofb_cast_bf16")
+    want16 = src.to(torch.bfloat16)
+    assert torch.equal(a16[:, :, :k], want16) and bool((a16[:, :, k:] == 0).all())
+    assert torch.equal(a16_t[:, :, :m], want16.transpose(1, 2)) and bool((a16_t[:, :, m:] == 0).all())
+    b16 = torch.zeros((batch, n, pk), dtype=torch.bfloat16, device="cuda")
+    b16[:, :, :k] = bop.to(torch.bfloat16)
+    ref = torch.bmm(a16[:, :, :k].float(), b16[:, :, :k].float().transpose(1, 2))
+    got = _gemm_nt((a16, k), (b16, k))
+    tol = 2e-3 * float(ref.abs().max()) + 1e-4
+    assert float((got - ref).abs().max()) <= tol
+    got2 = _gemm_nt((a16, k), (b16, k), accumulate_into=got.clone(), alpha=0.5)
+    assert float((got2 - 1.5 * ref).abs().max()) <= 1.5 * tol
+    # the transposed operand: D2 = src^T . X^T with X (n x m)
+    x16 = torch.zeros((batch, n, pm), dtype=torch.bfloat16, device="cuda")
+    x16[:, :, :m] = torch.randn((batch, n, m), device="cuda", generator=gen).to(torch.bfloat16)
+    ref2 = torch.bmm(a16_t[:, :, :m].float(), x16[:, :, :m].float().transpose(1, 2))
+    got3 = _gemm_nt((a16_t, m), (x16, m))
+    assert float((got3 - ref2).abs().max()) <= 2e-3 * float(ref2.abs().max()) + 1e-4
+
+
 def test_corr_block_backward(golden):
     """CorrBlock gradients with respect to the feature maps: the reference's autograd result (two lookups into one
     pyramid, tests/golden/corr_grad.npz), then other shapes / radii / level counts against autograd through
