@@ -490,17 +490,22 @@ def test_corr_block_backward(golden):
     from oracle import torch_port as tp
 
     g = golden("corr_grad")
-    f1, f2 = T(g["fmap1"]).requires_grad_(True), T(g["fmap2"]).requires_grad_(True)
-    blk = CorrBlock(f1, f2, num_levels=4, radius=4)
-    total = sum((blk(T(g[f"coords{k}"])) * T(g[f"weight{k}"])).sum() for k in range(2))
-    total.backward()
-    for got, want in ((N(f1.grad), g["dfmap1"]), (N(f2.grad), g["dfmap2"])):
-        assert maxabs(got, want) <= 2e-5 * np.abs(want).max()
-    assert blk._dpyr is None                                       # the gradient pyramid is freed once consumed
+    relnorm = lambda got, want: float(np.linalg.norm(got - want) / np.linalg.norm(want))
+    for dt in (torch.float32, torch.bfloat16):
+        f1, f2 = T(g["fmap1"]).requires_grad_(True), T(g["fmap2"]).requires_grad_(True)
+        blk = CorrBlock(f1, f2, num_levels=4, radius=4, pyramid_dtype=dt)
+        total = sum((blk(T(g[f"coords{k}"])) * T(g[f"weight{k}"])).sum() for k in range(2))
+        total.backward()
+        for got, want in ((N(f1.grad), g["dfmap1"]), (N(f2.grad), g["dfmap2"])):
+            if dt == torch.float32:                                   # fp32 pyramid -> fp32 GEMMs: fp32 summation noise
+                assert maxabs(got, want) <= 2e-5 * np.abs(want).max()
+            else:                                                     # default: bf16 operands on the tensor cores
+                assert relnorm(got, want) <= 6e-3
+        assert blk._dpyr is None                                      # the gradient pyramid is freed once consumed
 
     r = rng(51)
     for (b, c, h, w, lv, rad, dt) in [(1, 64, 9, 13, 2, 3, torch.bfloat16), (2, 32, 8, 20, 3, 2, torch.float32),
-                                      (1, 128, 24, 40, 4, 4, torch.bfloat16)]:
+                                      (1, 128, 24, 40, 4, 4, torch.bfloat16), (2, 48, 10, 11, 2, 4, torch.bfloat16)]:
         a1 = r.standard_normal((b, c, h, w)).astype(np.float32)
         a2 = r.standard_normal((b, c, h, w)).astype(np.float32)
         base = np.stack(np.meshgrid(np.arange(w), np.arange(h)), 0)[None].astype(np.float32)
@@ -512,8 +517,11 @@ def test_corr_block_backward(golden):
         g1, g2 = T(a1).requires_grad_(True), T(a2).requires_grad_(True)
         blk = CorrBlock(g1, g2, num_levels=lv, radius=rad, pyramid_dtype=dt)
         sum((blk(T(x)) * T(y)).sum() for x, y in zip(cs, ws)).backward()
-        assert maxabs(N(g1.grad), c1.grad.numpy()) <= 5e-5 * np.abs(c1.grad.numpy()).max(), (b, c, h, w, lv, rad)
-        assert maxabs(N(g2.grad), c2.grad.numpy()) <= 5e-5 * np.abs(c2.grad.numpy()).max(), (b, c, h, w, lv, rad)
+        for got, want in ((N(g1.grad), c1.grad.numpy()), (N(g2.grad), c2.grad.numpy())):
+            if dt == torch.float32 or c % 32:                         # fp32 GEMMs (also the fallback when C % 32 != 0)
+                assert maxabs(got, want) <= 5e-5 * np.abs(want).max(), (b, c, h, w, lv, rad)
+            else:
+                assert relnorm(got, want) <= 6e-3, (b, c, h, w, lv, rad)
     # bf16 GEMM operands (fp32 accumulation) for the feature-map gradients: mixed-precision tolerance
     os.environ["OFB200_BWD_GEMM"] = "bf16"
     try:

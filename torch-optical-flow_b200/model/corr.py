@@ -88,19 +88,51 @@ class _PyramidHandle(torch.autograd.Function):
                 for _ in range(blk.num_levels - 1):
                     cur = torch.nn.functional.avg_pool2d(cur, 2, stride=2)
                     levels.append(cur)
-            # GEMM precision: fp32 (default, matches the reference's fp32 autograd to 1e-5) or bf16 operands with
-            # fp32 accumulation (OFB200_BWD_GEMM=bf16: what a `precision: 16` run of the reference computes)
-            gemm_dt = torch.bfloat16 if os.environ.get("OFB200_BWD_GEMM", "fp32").lower() == "bf16" else torch.float32
-            f1g = f1.to(gemm_dt)
-            d1 = torch.zeros_like(f1)
+            # The two GEMMs per level.  "tcgen05" (default with a bf16 pyramid): bf16 operands, fp32 accumulation, this
+            # library's long-K tensor-core kernel fed by one cast / transpose pass over the fp32 gradient level --
+            # the precision of a `precision: 16` run of the reference.  "fp32" (default with an fp32 pyramid; matches
+            # the reference's fp32 autograd to 1e-5) and "bf16" go through the library bmm.  OFB200_BWD_GEMM overrides.
+            tc_ok = c % 32 == 0 and c <= 256
+            mode = os.environ.get("OFB200_BWD_GEMM", "").lower() or ("tcgen05" if blk._pyr.dtype == ofb200.DTYPE_BF16 and tc_ok else "fp32")
+            if mode == "tcgen05" and not tc_ok:
+                raise NotImplementedError("CorrBlock backward: the tcgen05 GEMM needs C to be a multiple of 32, at most 256")
             d_levels = []
-            for lvl, f2l in enumerate(levels):
-                hl, wl = f2l.shape[-2:]
-                dp = blk._dpyr[lvl].view(b, h * w, hl * wl).to(gemm_dt)              # (B, N, N_l), tight rows
-                f2g = f2l.detach().reshape(b, c, hl * wl).to(gemm_dt)
-                d1.add_(torch.bmm(f2g, dp.transpose(1, 2)).float(), alpha=scale)
-                d_levels.append((torch.bmm(f1g, dp).float() * scale).view(b, c, hl, wl))
-                blk._dpyr[lvl] = None                                               # free level by level
+            if mode == "tcgen05":
+                lib, st = ofb200.load(), ofb200.stream_ptr()
+                n = h * w
+                pn = (n + 7) // 8 * 8
+                d1t = torch.zeros((b, n, c), dtype=torch.float32, device=f1.device)            # d fmap1^T, summed over levels
+                f1_16 = torch.zeros((b, c, pn), dtype=torch.bfloat16, device=f1.device)
+                f1_16[:, :, :n] = f1
+                for lvl, f2l in enumerate(levels):
+                    hl, wl = f2l.shape[-2:]
+                    nl = hl * wl
+                    pk = (nl + 7) // 8 * 8
+                    a16 = torch.empty((b, n, pk), dtype=torch.bfloat16, device=f1.device)      # bf16(dP_l)
+                    a16_t = torch.empty((b, nl, pn), dtype=torch.bfloat16, device=f1.device)   # bf16(dP_l)^T
+                    ofb200.check(lib.ofb_cast_bf16(ofb200.ptr(blk._dpyr[lvl]), ofb200.ptr(a16), ofb200.ptr(a16_t), b, n, nl,
+                                                   pk, pn, st), "ofb_cast_bf16")
+                    blk._dpyr[lvl] = None                                                       # free level by level
+                    f2_16 = torch.zeros((b, c, pk), dtype=torch.bfloat16, device=f1.device)
+                    f2_16[:, :, :nl] = f2l.detach().reshape(b, c, nl)
+                    ofb200.check(lib.ofb_gemm_nt_bf16(ofb200.ptr(a16), ofb200.ptr(f2_16), ofb200.ptr(d1t), b, n, c, nl, pk, pk, c,
+                                                      n * pk, c * pk, n * c, scale, 1, st), "ofb_gemm_nt_bf16")
+                    d2t = torch.empty((b, nl, c), dtype=torch.float32, device=f1.device)
+                    ofb200.check(lib.ofb_gemm_nt_bf16(ofb200.ptr(a16_t), ofb200.ptr(f1_16), ofb200.ptr(d2t), b, nl, c, n, pn, pn, c,
+                                                      nl * pn, c * pn, nl * c, scale, 0, st), "ofb_gemm_nt_bf16")
+                    d_levels.append(d2t.transpose(1, 2).reshape(b, c, hl, wl))
+                d1 = d1t.transpose(1, 2).contiguous()
+            else:
+                gemm_dt = torch.bfloat16 if mode == "bf16" else torch.float32
+                f1g = f1.to(gemm_dt)
+                d1 = torch.zeros_like(f1)
+                for lvl, f2l in enumerate(levels):
+                    hl, wl = f2l.shape[-2:]
+                    dp = blk._dpyr[lvl].view(b, h * w, hl * wl).to(gemm_dt)              # (B, N, N_l), tight rows
+                    f2g = f2l.detach().reshape(b, c, hl * wl).to(gemm_dt)
+                    d1.add_(torch.bmm(f2g, dp.transpose(1, 2)).float(), alpha=scale)
+                    d_levels.append((torch.bmm(f1g, dp).float() * scale).view(b, c, hl, wl))
+                    blk._dpyr[lvl] = None                                               # free level by level
             d2 = torch.autograd.grad(levels, leaf, d_levels)[0]
             d1 = d1.view(b, c, h, w).to(fmap1.dtype)
             d2 = d2.to(fmap2.dtype)
