@@ -232,7 +232,7 @@ def bench_corr_train_c4(b=4, iters=12):
     coords = [(base + 3 * torch.randn((b, 2, h, w), device="cuda", generator=gen)).contiguous() for _ in range(iters)]
     wts = [torch.randn((b, 324, h, w), device="cuda", generator=gen) for _ in range(iters)]
     recs = []
-    for mode in ("fp32", "bf16"):
+    for mode in ("fp32", "bf16", "tcgen05"):
         os.environ["OFB200_BWD_GEMM"] = mode
         times = {"fwd": [], "bwd": []}
         for rep in range(4):
