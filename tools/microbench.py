@@ -255,6 +255,29 @@ def bench_corr_train_c4(b=4, iters=12):
     return recs
 
 
+def bench_gemm_nt(shapes=((16, 7332, 256, 7332), (8, 32640, 256, 32640), (16, 7332, 256, 1833))):
+    """The backward GEMM kernel alone: D[M x N] = A[M x K] . B[N x K]^T, bf16 in, fp32 out (level-0 shapes of C4 / C5)."""
+    lib = ofb200.load()
+    recs = []
+    for (b, m, n, k) in shapes:
+        gen = torch.Generator(device="cuda").manual_seed(2)
+        pk = (k + 7) // 8 * 8
+        a = torch.randn((b, m, pk), device="cuda", generator=gen).to(torch.bfloat16)
+        bb = torch.randn((b, n, pk), device="cuda", generator=gen).to(torch.bfloat16)
+        d = torch.empty((b, m, n), device="cuda")
+
+        def run():
+            rc = lib.ofb_gemm_nt_bf16(ofb200.ptr(a), ofb200.ptr(bb), ofb200.ptr(d), b, m, n, k, pk, pk, n, m * pk, n * pk, m * n,
+                                      1.0, 0, ofb200.stream_ptr())
+            assert rc == 0
+        ms = timeit(run)
+        flops = 2.0 * b * m * n * k
+        recs.append({"kernel": f"backward GEMM B{b} M{m} N{n} K{k} (bf16 -> fp32)", "ms": round(ms, 4),
+                     "tflops": round(flops / ms / 1e9, 1), "tensor_frac_sustained": round(flops / ms / 1e9 / 1391.6, 3),
+                     "gbs_A_stream": round(b * m * pk * 2 / ms / 1e6, 1)})
+    return recs
+
+
 def bench_sequence_loss_c4(n_pred=12):
     """sequence_loss over 12 full-resolution predictions at the C4 (KITTI) size: 8 B/px per prediction + 12 B/px."""
     import ctypes
