@@ -314,7 +314,7 @@ def run_ours(args):
         for v in views:
             lo = lookup_out if v["fmap1"].shape[0] == micro else None
             hot_path(v, metric, timers=timers, lookup_out=lo, cta_group=args.cta_group)
-        metric.sync()                                  # (sum, count) all-reduce: the only collective
+        return metric.sync()                           # (sum, count) all-reduce of a copy: the only collective
 
     # ---- device-resident arm
     for _ in range(args.warmup):

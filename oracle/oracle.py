@@ -220,10 +220,12 @@ def corr_pyramid(fmap1, fmap2, num_levels=4):
     return pyr
 
 
-def corr_lookup(pyramid, coords, radius=4, return_index=False):
+def corr_lookup(pyramid, coords, radius=4, return_index=False, shared_slice=False):
     """pyramid: list of (B*h*w, 1, h_l, w_l) float32; coords (B,2,h,w) -> (B, L*(2r+1)^2, h, w).
 
     With return_index=True also returns idx (Q,L,2,2r+1) int32 and valid (Q,L,(2r+1)^2) u8.
+    shared_slice=True: the levels are (1, 1, h_l, w_l) and every query reads the same slice (query stride 0) --
+    for checks of the floor indices / validity masks of many queries, which do not depend on the volume.
     """
     coords = _f32(coords)
     b, two, h, w = coords.shape
@@ -233,7 +235,8 @@ def corr_lookup(pyramid, coords, radius=4, return_index=False):
     d = 2 * radius + 1
     q = b * h * w
     ptrs = (_c_f * L)(*[_p(p) for p in pyr])
-    qs = (ctypes.c_int64 * L)(*[p.shape[2] * p.shape[3] for p in pyr])
+    qs = (ctypes.c_int64 * L)(*[0 if shared_slice else p.shape[2] * p.shape[3] for p in pyr])
+    assert all(p.shape[0] == (1 if shared_slice else q) for p in pyr)
     rp = (ctypes.c_int * L)(*[p.shape[3] for p in pyr])
     lh = (ctypes.c_int * L)(*[p.shape[2] for p in pyr])
     lw = (ctypes.c_int * L)(*[p.shape[3] for p in pyr])

@@ -1,5 +1,5 @@
 """world_size-2 gloo tests (CPU) of the multi-GPU host logic: contiguous pair sharding and the
-(sum_epe, total) all-reduce behind AverageEndPointError.sync() -- the dist_reduce_fx="sum" semantics
+(sum_epe, total) all-reduce behind AverageEndPointError.sync() / compute() -- the dist_reduce_fx="sum" semantics
 of the reference's optical_flow/metrics/epe.py:22-23.  The per-rank metric state is what the K4c
 kernel would have accumulated on that rank's shard; here the CPU oracle produces it."""
 import os
@@ -39,10 +39,20 @@ def _worker(rank, world, port, total_pairs, q):
         lo, hi = shard_range(total_pairs, rank, world)
         s, n = oracle.epe_sum_count(pred[lo:hi], target[lo:hi], valid[lo:hi]) if hi > lo else (0.0, 0)
         m = AverageEndPointError()
-        m._acc = torch.tensor([s, float(n)], dtype=torch.float64)      # state the kernel leaves on this rank
-        m.sync()
+        if hi > lo:                                                    # a rank with an empty shard never calls update():
+            m._acc = torch.tensor([s, float(n)], dtype=torch.float64)  # it must still take part in the collective
+        g1 = m.sync()
+        g2 = m.sync()                                                  # idempotent: the local state is not modified
+        assert torch.equal(g1, g2)
+        local = m._state().clone()
+        assert float(local[0]) == s and int(local[1]) == n
         gs, gn = oracle.epe_sum_count(pred, target, valid)
-        q.put((rank, lo, hi, float(m.compute()), gs / gn, int(m.total), gn))
+        first = float(m.compute())
+        # update -> sync -> update -> sync: a second batch (the same shard again) doubles both states exactly
+        m._state().add_(torch.tensor([s, float(n)], dtype=torch.float64))
+        g3 = m.sync()
+        assert float(g3[1]) == 2 * gn and abs(float(g3[0]) - 2 * gs) <= 1e-9 * max(1.0, gs)
+        q.put((rank, lo, hi, first, gs / gn, int(g1[1]), gn))
     finally:
         dist.destroy_process_group()
 

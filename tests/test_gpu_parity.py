@@ -97,7 +97,7 @@ def test_warp_options_golden(golden, mode, pad, ac):
     for variant in ([1] if mode == "nearest" else warp_variants(g["opt_frame"].shape[-1])):
         out = N(warp(T(g["opt_frame"]), T(g["opt_flow"]), mode=mode, padding_mode=pad, align_corners=ac, variant=variant))
         if mode == "nearest":
-            assert np.mean(out != ref) <= 0.005
+            assert np.array_equal(out, ref)                               # index work: exact
         else:
             assert maxabs(out, ref) <= 1e-5, variant
 
@@ -263,6 +263,38 @@ def test_warp_full_size_properties():
     assert float((ident - frame).abs().max()) <= 2e-4       # ulp(1023) = 6e-5 on the source coordinate
     out, mask = warp(frame, torch.zeros_like(flow), return_mask=True)
     assert int(mask.sum()) == b * (h - 2) * (w - 2)          # border pixels sit exactly on -1 / +1
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 436, 1024), (1, 3, 1088, 1920)])
+@pytest.mark.parametrize("pad", ["border", "zeros"])
+def test_warp_full_size_vs_oracle(shape, pad):
+    """BASELINE shapes against the CPU oracle: the Sintel frame of C2 (two of its 32 images) and the 1088x1920
+    frame of C5 -- W = 1920 is where a non-fused coordinate un-normalisation is 5.8e-5 off (SURVEY.md "five things"
+    #3; reference operator.py:30).  Every kernel variant, pixel-unit flow both ways (normalize() then warp, and the
+    fused pixel_flow path), validity mask bit-exact, values <= 1e-5."""
+    from optical_flow import normalize, warp
+
+    r = rng(31)
+    b, c, h, w = shape
+    frame = r.random(shape, dtype=np.float32)
+    flow_px = (5.0 * r.standard_normal((b, 2, h, w))).astype(np.float32)
+    flow_px[:, :, : h // 8] *= 12.0                      # a band of +-60 px flows: taps far outside any staged window
+    flow = oracle.normalize(flow_px).astype(np.float32)
+    ref, ref_mask = oracle.warp(frame, flow, padding_mode=pad, return_mask=True)
+    frame_d, flow_d = T(frame), T(flow)
+    assert maxabs(N(normalize(T(flow_px))), flow) == 0.0
+    first = None
+    for variant in warp_variants(w):
+        out, mask = warp(frame_d, flow_d, padding_mode=pad, return_mask=True, variant=variant)
+        out = N(out)
+        assert maxabs(out, ref) <= 1e-5, variant
+        assert np.array_equal(N(mask).astype(np.uint8), ref_mask), variant
+        if first is None:
+            first = out
+        else:
+            assert np.array_equal(first, out), variant
+    fused, fmask = warp(frame_d, T(flow_px), padding_mode=pad, return_mask=True, pixel_flow=True)
+    assert np.array_equal(N(fused), first) and np.array_equal(N(fmask).astype(np.uint8), ref_mask)
 
 
 def test_warp_errors():
@@ -1080,6 +1112,92 @@ def test_corr_pyramid_full_size_properties():
     v = blk.corr_pyramid[0].view(b, h * w, h, w)[bsel].reshape(h * w, h * w).float()
     vt = blk_t.corr_pyramid[0].view(b, h * w, h, w)[bsel].reshape(h * w, h * w).float()
     assert float((v - vt.t()).abs().max()) <= 0.05
+
+
+def _sampled_rows_fp32(f1, f2, q):
+    """fp32 rows q of corr = fmap1^T . fmap2 / sqrt(C) (reference corr.py:82-87), one matmul per batch element."""
+    b, c, h, w = f1.shape
+    n = h * w
+    out = torch.empty((q.numel(), n), dtype=torch.float32, device=f1.device)
+    qb, qp = q // n, q % n
+    for bi in range(b):
+        sel = (qb == bi).nonzero().flatten()
+        if sel.numel():
+            a = f1.view(b, c, n)[bi][:, qp[sel]].t().contiguous()          # (k, C)
+            out[sel] = (a @ f2.view(b, c, n)[bi]) / float(c) ** 0.5
+    return out.view(-1, h, w)
+
+
+def test_corr_pyramid_c5_bench_shape_vs_fp32():
+    """The bench shape (C5 micro-batch: 256 ch, 136x240, two pairs): sampled query rows of every level against an fp32
+    recomputation (level 0) and the means of complete 2^l x 2^l blocks of it (levels 1-3; 136 = 8 * 17 exercises the
+    floor of reference corr.py:52-54 on the last level: 17 x 30), plus a CPU-oracle cross-check of a few rows."""
+    from model.corr import CorrBlock
+
+    b, c, h, w = 2, 256, 136, 240
+    gen = torch.Generator(device="cuda").manual_seed(41)
+    f1 = torch.randn((b, c, h, w), device="cuda", generator=gen)
+    f2 = torch.randn((b, c, h, w), device="cuda", generator=gen)
+    blk = CorrBlock(f1, f2)
+    assert blk.builder == "tcgen05"
+    torch.cuda.synchronize()
+    n = h * w
+    corners = torch.tensor([0, w - 1, n - w, n - 1, n, 2 * n - 1, n + 127, n + 128, 32639, 32640 - 241], device="cuda")
+    q = torch.cat([corners, torch.randint(0, b * n, (758,), device="cuda", generator=gen)])
+    ref0 = _sampled_rows_fp32(f1, f2, q)
+    assert [tuple(p.shape[-2:]) for p in blk.corr_pyramid] == [(136, 240), (68, 120), (34, 60), (17, 30)]
+    for lvl in range(4):
+        k = 2 ** lvl
+        hl, wl = h // k, w // k
+        want = ref0[:, : hl * k, : wl * k].reshape(-1, hl, k, wl, k).mean(dim=(2, 4))
+        got = blk.corr_pyramid[lvl][q, 0].float()
+        assert got.shape == want.shape
+        rel = float((got - want).norm() / want.norm())
+        mx = float((got - want).abs().max() / want.pow(2).mean().sqrt())
+        assert rel <= 4e-3 and mx <= 4e-2, (lvl, rel, mx)
+    # the fp32 recomputation itself against the CPU oracle's sgemm (reference op order) on 6 rows
+    f1n, f2n = N(f1), N(f2)
+    for qi in (0, 9, 100):
+        qq = int(q[qi]); bi, p = divmod(qq, n)
+        row = (f1n[bi].reshape(c, n)[:, p] @ f2n[bi].reshape(c, n)) / np.float32(16.0)
+        assert maxabs(N(ref0[qi]).ravel(), row) <= 2e-4
+
+
+@pytest.mark.parametrize("kind", ["int", "noise", "edge"])
+def test_lookup_c5_bench_shape_on_stored_pyramid(kind):
+    """K3 at 136x240 on the pyramid the tcgen05 builder stored (query-minor 8x4 blocks): floor indices and validity
+    masks bit-exact for EVERY query, values <= 1e-5 against the CPU oracle run on the GPU's own stored levels for
+    2048 sampled queries (the oracle needs fp32 slices: 131 KB per query and level 0)."""
+    from model.corr import CorrBlock
+
+    b, c, h, w = 1, 256, 136, 240
+    gen = torch.Generator(device="cuda").manual_seed(43)
+    f1 = torch.randn((b, c, h, w), device="cuda", generator=gen)
+    f2 = torch.randn((b, c, h, w), device="cuda", generator=gen)
+    blk = CorrBlock(f1, f2)
+    r = rng(44)
+    coords = oracle.coords_grid(b, h, w)
+    if kind == "noise":
+        coords = (coords + 4 * r.standard_normal(coords.shape)).astype(np.float32)
+    if kind == "edge":
+        coords[:, 0] = np.where(coords[:, 0] < w / 2, coords[:, 0] * 0.1 - 3.0, w - 1 + coords[:, 0] * 0.05)
+        coords[:, 1] = np.where(coords[:, 1] < h / 2, -2.0, h + 1.25)
+        coords = coords.astype(np.float32)
+    out, idx, valid = blk(T(coords), return_index=True)
+    out, idx, valid = N(out), N(idx), N(valid)
+    n = h * w
+    sel = np.unique(np.concatenate([[0, w - 1, n - w, n - 1, n // 2], r.integers(0, n, 2043)]))
+    sel_d = torch.from_numpy(sel).cuda()
+    levels = [N(blk.corr_pyramid[l][sel_d].float()) for l in range(4)]
+    csel = coords.reshape(1, 2, n)[:, :, sel].reshape(1, 2, 1, sel.size)
+    ref, ridx, rvalid = oracle.corr_lookup(levels, csel, radius=4, return_index=True)
+    assert np.array_equal(idx[sel], ridx) and np.array_equal(valid[sel], rvalid)
+    got = out.reshape(324, n)[:, sel]
+    assert maxabs(got, ref.reshape(324, sel.size)) <= tol(ref)
+    # indices / masks of all queries: a pyramid of the same level sizes carries no values into them
+    zeros = [np.zeros((1, 1, h >> l, w >> l), np.float32) for l in range(4)]
+    _, ridx, rvalid = oracle.corr_lookup(zeros, coords, radius=4, return_index=True, shared_slice=True)
+    assert np.array_equal(idx, ridx) and np.array_equal(valid, rvalid)
 
 
 # =============================================================================== RAFT.forward trace

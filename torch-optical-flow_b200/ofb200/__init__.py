@@ -187,3 +187,16 @@ def forward_only(fn, name, *tensors):
     if torch.is_grad_enabled() and any(t.requires_grad for t in tensors):
         return _NoBackward.apply(fn, name, *tensors)
     return fn(*tensors)
+
+
+def patch_reference(*args, **kwargs):
+    """Rebind the hot-path names of an already-imported reference checkout to these kernels (ofb200/overlay.py)."""
+    from ofb200.overlay import patch_reference as _patch
+
+    return _patch(*args, **kwargs)
+
+
+def unpatch_reference():
+    from ofb200.overlay import unpatch_reference as _unpatch
+
+    return _unpatch()

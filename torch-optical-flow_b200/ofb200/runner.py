@@ -19,10 +19,10 @@ from typing import Dict, List, Optional
 import torch
 from torch import Tensor
 
-from model.corr import CorrBlock
-from model.raft import upsample_flow
-from optical_flow.metrics.epe import AverageEndPointError
-from optical_flow.operator.operator import warp
+from ofb200.ops.corr import CorrBlock
+from ofb200.ops.epe import AverageEndPointError
+from ofb200.ops.operator import warp
+from ofb200.ops.raft_ops import upsample_flow
 
 FIELDS = ("fmap1", "fmap2", "coords", "flow_lo", "up_mask", "frame", "target", "valid")
 
@@ -73,7 +73,7 @@ class _NoSpan:
 def hot_path(batch: Dict[str, Tensor], metric: AverageEndPointError, timers: Optional[KernelTimers] = None,
              lookup_out: Optional[Tensor] = None, cta_group: int = 0) -> Dict[str, Tensor]:
     """Run the pass on device tensors.  `batch["coords"]` is (iters, B, 2, h, w)."""
-    import model.corr as corr_mod
+    import ofb200.ops.corr as corr_mod
 
     sp = (lambda n, k: timers.span(n, k)) if timers is not None else (lambda n, k: _NoSpan())
     corr_mod.TIMERS = timers                       # CorrBlock brackets its prep launches and the pyramid kernel itself
@@ -230,8 +230,7 @@ class HostStagedRunner:
             hot_path(dev, metric, lookup_out=self.lookup_out)
             self.freed[slot].record(cur)
         self._slot = (first + len(chunks)) & 1
-        metric.sync()
-        state = metric._acc.cpu()                               # device -> host read of the step's result
+        state = metric.sync().cpu()                             # all-reduced COPY of (sum, count), read back to the host
         self.d2h_bytes += state.numel() * state.element_size()
         return float(state[0] / state[1])
 
@@ -260,8 +259,7 @@ class HostStagedRunner:
                 self.lookup_out = torch.empty((b, 324, h, w), dtype=torch.float32, device=self.device)
             hot_path(dev, metric, lookup_out=self.lookup_out)
             self.freed[slot].record(cur)
-        metric.sync()
-        state = metric._acc.cpu()                        # device -> host read of the step's result
+        state = metric.sync().cpu()                      # all-reduced COPY of (sum, count), read back to the host
         self.d2h_bytes += state.numel() * state.element_size()
         return float(state[0] / state[1])
 
