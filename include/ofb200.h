@@ -15,8 +15,8 @@
  *   - the last argument is the CUDA stream (cudaStream_t passed as void*; NULL = default)
  *   - returns 0 on success, a negative OFB_E* code for a rejected argument, or a positive
  *     cudaError_t for a CUDA failure; never throws, never allocates device memory, never
- *     synchronises (ofb_corr_plan_* are the only calls that touch the driver outside a
- *     stream: they encode TMA descriptors on the host)
+ *     synchronises (ofb_corr_pyramid_bf16*, ofb_gemm_nt_bf16 and the TMA variant of ofb_warp_f32 are the only
+ *     calls that touch the driver outside a stream: they encode TMA descriptors on the host)
  *   - there is no CPU compute path: without a CUDA device every call fails
  */
 #ifndef OFB200_H_
@@ -44,6 +44,7 @@ extern "C" {
 
 #define OFB_DTYPE_F32 0
 #define OFB_DTYPE_BF16 1
+#define OFB_DTYPE_F16 2 /* input feature maps of ofb_corr_prep_from only */
 
 #define OFB_MAX_LEVELS 4
 
@@ -216,6 +217,12 @@ int ofb_pyramid_layout(int h, int w, int levels, int mode, ofb_pyramid* pyr_host
  *         on-device cross-check and for shapes the tensor-core kernel rejects.
  * ------------------------------------------------------------------------------------- */
 int ofb_corr_prep_bf16(const float* fmap_nchw, void* out_km_bf16, int B, int C, int h, int w, int pool,
+                       float scale, void* stream);
+/* The same pass reading the feature map in its own precision: in_dtype OFB_DTYPE_F32, OFB_DTYPE_BF16 or
+ * OFB_DTYPE_F16.  The reference's shipped configs run `precision: 16` (methods/raft/config/train/default.yaml:20) and
+ * raft.py:110-111 answers with fmap.float() -- a full extra pass and twice the bytes for maps whose values are half
+ * precision anyway; here the half-precision map is the kernel's input (element -> fp32 -> * scale -> bf16). */
+int ofb_corr_prep_from(const void* fmap_nchw, int in_dtype, void* out_km_bf16, int B, int C, int h, int w, int pool,
                        float scale, void* stream);
 int ofb_corr_pyramid_bf16(const void* f1_km, const void* f2_km, const void* f2q_km, const ofb_pyramid* pyr_host,
                           int B, int C, int h, int w, float scale, int cta_group, void* stream);

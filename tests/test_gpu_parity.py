@@ -533,7 +533,7 @@ def test_corr_block_backward(golden):
                 assert maxabs(got, want) <= 2e-5 * np.abs(want).max()
             else:                                                     # default: bf16 operands on the tensor cores
                 assert relnorm(got, want) <= 6e-3
-        assert blk._dpyr is None                                      # the gradient pyramid is freed once consumed
+        assert blk._grad.dpyr is None                                 # the gradient pyramid is freed once consumed
 
     r = rng(51)
     for (b, c, h, w, lv, rad, dt) in [(1, 64, 9, 13, 2, 3, torch.bfloat16), (2, 32, 8, 20, 3, 2, torch.float32),
@@ -571,6 +571,66 @@ def test_corr_block_backward(golden):
         assert not blk(T(cs[0])).requires_grad
     (blk(T(cs[0])) * T(ws[0])).sum().backward()
     assert g2.grad is not None and bool(torch.isfinite(g2.grad).all())
+
+
+def test_corr_block_autograd_holds_no_block_and_drops_stale_gradients():
+    """(1) the autograd contexts keep a small state object, not the CorrBlock -- dropping the last user
+    reference frees the block (and its multi-GB pyramid) at once, without the cyclic collector; (2) a gradient pyramid
+    left behind by another backward pass (one that raised, or never reached the handle node) is not accumulated into."""
+    import gc
+    import weakref
+
+    from model import CorrBlock
+    from model.utils import coords_grid
+
+    gen = torch.Generator(device="cuda").manual_seed(61)
+    f1 = torch.randn((1, 64, 16, 24), device="cuda", generator=gen, requires_grad=True)
+    f2 = torch.randn((1, 64, 16, 24), device="cuda", generator=gen, requires_grad=True)
+    coords = coords_grid(1, 16, 24).cuda() + torch.randn((1, 2, 16, 24), device="cuda", generator=gen)
+    wgt = torch.randn((1, 324, 16, 24), device="cuda", generator=gen)
+    gc.collect()
+    gc.disable()
+    try:
+        blk = CorrBlock(f1, f2)
+        out = blk(coords)
+        alive = weakref.ref(blk)
+        del blk
+        assert alive() is None, "CorrBlock is kept alive by its own autograd graph (reference cycle)"
+        (out * wgt).sum().backward()                       # the graph still works without the block
+    finally:
+        gc.enable()
+    clean1, clean2 = f1.grad.clone(), f2.grad.clone()
+    f1.grad = f2.grad = None
+    blk = CorrBlock(f1, f2)
+    out = blk(coords)
+    st = blk._grad
+    st.alloc()
+    for t in st.dpyr:
+        t.fill_(7.0)                                       # what an aborted backward would have left behind
+    st.task = -12345
+    (out * wgt).sum().backward()
+    assert torch.equal(f1.grad, clean1) and torch.equal(f2.grad, clean2)
+    assert st.dpyr is None
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_corr_block_half_precision_feature_maps(dt):
+    """`precision: 16` callers (reference methods/raft/config/train/default.yaml:20): the prep kernel reads bf16 / fp16
+    maps directly.  Same bits as handing over the same values in fp32 (1/sqrt(C) is a power of two for C = 64, 256)."""
+    from model.corr import CorrBlock
+
+    gen = torch.Generator(device="cuda").manual_seed(62)
+    for (b, c, h, w) in [(2, 256, 24, 40), (1, 64, 19, 37)]:
+        f1 = torch.randn((b, c, h, w), device="cuda", generator=gen).to(dt)
+        f2 = torch.randn((b, c, h, w), device="cuda", generator=gen).to(dt)
+        half = CorrBlock(f1, f2)
+        full = CorrBlock(f1.float(), f2.float())
+        assert half.builder == "tcgen05"
+        for a, bb in zip(half.corr_pyramid, full.corr_pyramid):
+            assert torch.equal(a, bb)
+        ref = oracle.corr_pyramid(N(f1.float()), N(f2.float()), 4)
+        for (rel, mx) in _pyr_errors(half.corr_pyramid, ref):
+            assert rel <= 4e-3 and mx <= 4e-2
 
 
 def test_empty_batches():

@@ -20,8 +20,17 @@ constexpr int TCMAX = 256;  // channels per tile (the whole K extent of the tens
 
 // One CTA turns a 32-pixel x C-channel tile: reads are 128-byte lines (32 pixels of one channel), 8 in
 // flight per thread; writes are whole 2*C-byte pixel rows of the K-major operand.
-template <int POOL>
-__global__ void __launch_bounds__(256) prep_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int C,
+// feature-map element -> fp32: the maps arrive in fp32, or in half precision from an autocast (`precision: 16`) caller
+__device__ __forceinline__ float ld_in(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ld_in(const __nv_bfloat16* p) {
+    return __uint_as_float((unsigned)__ldg(reinterpret_cast<const unsigned short*>(p)) << 16);
+}
+__device__ __forceinline__ float ld_in(const __half* p) {
+    return __half2float(__ushort_as_half(__ldg(reinterpret_cast<const unsigned short*>(p))));
+}
+
+template <int POOL, typename TIn>
+__global__ void __launch_bounds__(256) prep_kernel(const TIn* __restrict__ in, __nv_bfloat16* __restrict__ out, int C,
                                                    int h, int w, float scale) {
     // output pixel p = (yo, xo) of the (h/POOL) x (w/POOL) image = mean of a complete POOL x POOL block
     extern __shared__ float tile[];                       // [Ct][TP + 1]
@@ -31,7 +40,7 @@ __global__ void __launch_bounds__(256) prep_kernel(const float* __restrict__ in,
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int p = p0 + lane;
     const int yo = p / wo, xo = p - yo * wo;
-    const float* src0 = in + ((size_t)b * C + c0) * HW + (size_t)(yo * POOL) * w + xo * POOL;
+    const TIn* src0 = in + ((size_t)b * C + c0) * HW + (size_t)(yo * POOL) * w + xo * POOL;
     const bool pok = p < HWo;
     for (int cb = warp; cb < Ct; cb += 64) {              // 8 warps x 8 independent channel rows per pass
         float v[8];
@@ -40,15 +49,15 @@ __global__ void __launch_bounds__(256) prep_kernel(const float* __restrict__ in,
             const int c = cb + 8 * u;
             v[u] = 0.0f;
             if (pok && c < Ct) {
-                const float* src = src0 + (size_t)c * HW;
+                const TIn* src = src0 + (size_t)c * HW;
                 if (POOL == 1) {
-                    v[u] = __ldg(src);
+                    v[u] = ld_in(src);
                 } else {
                     float a = 0.0f;
 #pragma unroll
                     for (int dy = 0; dy < POOL; ++dy)
 #pragma unroll
-                        for (int dx = 0; dx < POOL; ++dx) a += __ldg(src + dy * w + dx);
+                        for (int dx = 0; dx < POOL; ++dx) a += ld_in(src + dy * w + dx);
                     v[u] = a * (1.0f / (float)(POOL * POOL));
                 }
             }
@@ -161,23 +170,40 @@ int build_simt(const float* f1, const float* f2, const ofb_pyramid* pyr, int B, 
 
 }  // namespace
 
-OFB_API int ofb_corr_prep_bf16(const float* fmap_nchw, void* out_km_bf16, int B, int C, int h, int w, int pool,
+template <typename TIn>
+static int launch_prep(const void* fmap, __nv_bfloat16* out, int B, int C, int h, int w, int pool, float scale, int HWo,
+                       cudaStream_t st) {
+    dim3 grid((HWo + TP - 1) / TP, (C + TCMAX - 1) / TCMAX, B);
+    const size_t smem = (size_t)(C < TCMAX ? C : TCMAX) * (TP + 1) * sizeof(float);      // <= 33 KiB
+    const TIn* in = reinterpret_cast<const TIn*>(fmap);
+    if (pool == 1) prep_kernel<1, TIn><<<grid, 256, smem, st>>>(in, out, C, h, w, scale);
+    else prep_kernel<4, TIn><<<grid, 256, smem, st>>>(in, out, C, h, w, scale);
+    OFB_LAUNCH_CHECK();
+    return OFB_OK;
+}
+
+OFB_API int ofb_corr_prep_from(const void* fmap_nchw, int in_dtype, void* out_km_bf16, int B, int C, int h, int w, int pool,
                                float scale, void* stream) {
     if (B == 0) return OFB_OK;   // nothing to do: empty tensors have no storage, their pointers may be null
     if (!fmap_nchw || !out_km_bf16 || B < 0 || C <= 0 || h <= 0 || w <= 0) return OFB_EINVAL;
     if (pool != 1 && pool != 4) return OFB_EINVAL;
+    if (in_dtype != OFB_DTYPE_F32 && in_dtype != OFB_DTYPE_BF16 && in_dtype != OFB_DTYPE_F16) return OFB_EINVAL;
     if (C & 1) return OFB_EUNSUPPORTED;
     if (reinterpret_cast<uintptr_t>(out_km_bf16) & 3) return OFB_EALIGN;
+    if (reinterpret_cast<uintptr_t>(fmap_nchw) & (in_dtype == OFB_DTYPE_F32 ? 3 : 1)) return OFB_EALIGN;
     const int HWo = (h / pool) * (w / pool);
-    if (B == 0 || HWo == 0) return OFB_OK;
+    if (HWo == 0) return OFB_OK;
     if (B > 65535) return OFB_EUNSUPPORTED;
-    dim3 grid((HWo + TP - 1) / TP, (C + TCMAX - 1) / TCMAX, B);
-    const size_t smem = (size_t)(C < TCMAX ? C : TCMAX) * (TP + 1) * sizeof(float);      // <= 33 KiB
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(out_km_bf16);
-    if (pool == 1) prep_kernel<1><<<grid, 256, smem, (cudaStream_t)stream>>>(fmap_nchw, out, C, h, w, scale);
-    else prep_kernel<4><<<grid, 256, smem, (cudaStream_t)stream>>>(fmap_nchw, out, C, h, w, scale);
-    OFB_LAUNCH_CHECK();
-    return OFB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (in_dtype == OFB_DTYPE_F32) return launch_prep<float>(fmap_nchw, out, B, C, h, w, pool, scale, HWo, st);
+    if (in_dtype == OFB_DTYPE_BF16) return launch_prep<__nv_bfloat16>(fmap_nchw, out, B, C, h, w, pool, scale, HWo, st);
+    return launch_prep<__half>(fmap_nchw, out, B, C, h, w, pool, scale, HWo, st);
+}
+
+OFB_API int ofb_corr_prep_bf16(const float* fmap_nchw, void* out_km_bf16, int B, int C, int h, int w, int pool,
+                               float scale, void* stream) {
+    return ofb_corr_prep_from(fmap_nchw, OFB_DTYPE_F32, out_km_bf16, B, C, h, w, pool, scale, stream);
 }
 
 OFB_API int ofb_pyramid_layout(int h, int w, int levels, int mode, ofb_pyramid* pyr, int64_t elems[OFB_MAX_LEVELS]) {

@@ -17,7 +17,7 @@ CSRC = os.path.join(os.path.dirname(_HERE), "csrc")
 
 MODE = {"bilinear": 0, "nearest": 1}
 PAD = {"zeros": 0, "border": 1, "reflection": 2}
-DTYPE_F32, DTYPE_BF16 = 0, 1
+DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
 LAYOUT_ROWS, LAYOUT_BLOCK8X4, LAYOUT_QMINOR8X4 = 0, 1, 2
 MAX_LEVELS = 4
 
@@ -65,6 +65,7 @@ SIGNATURES = {
     "ofb_sequence_loss_f32": (_i, [ctypes.POINTER(_vp), _i, _vp, _vp, _vp, _i, _i, _i, ctypes.c_double, _f, _vp]),
     "ofb_pyramid_layout": (_i, [_i, _i, _i, _i, ctypes.POINTER(Pyramid), ctypes.POINTER(_i64 * MAX_LEVELS)]),
     "ofb_corr_prep_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
+    "ofb_corr_prep_from": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "ofb_corr_pyramid_bf16": (_i, [_vp, _vp, _vp, ctypes.POINTER(Pyramid), _i, _i, _i, _i, _f, _i, _vp]),
     "ofb_corr_pyramid_bf16_profile": (_i, [_vp, _vp, _vp, ctypes.POINTER(Pyramid), _i, _i, _i, _i, _f, _i, _vp, _vp]),
     "ofb_corr_pyramid_simt_f32": (_i, [_vp, _vp, ctypes.POINTER(Pyramid), _i, _i, _i, _i, _f, _vp]),

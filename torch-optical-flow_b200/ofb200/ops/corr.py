@@ -41,10 +41,15 @@ def _span(name: str, launches: int):
     return TIMERS.span(name, launches) if TIMERS is not None else _NullSpan()
 
 
+_IN_DTYPES = {torch.float32: ofb200.DTYPE_F32, torch.bfloat16: ofb200.DTYPE_BF16, torch.float16: ofb200.DTYPE_F16}
+
+
 def prepare_operands(fmap1: Tensor, fmap2: Tensor, num_levels: int):
     """K-major bf16 operands of the tcgen05 builder: fmap1 * 1/sqrt(C), fmap2, and (for pyramids with
-    more than two levels) fmap2 averaged over complete 4x4 blocks.  fp32 (B, C, h, w) CUDA inputs."""
+    more than two levels) fmap2 averaged over complete 4x4 blocks.  (B, C, h, w) CUDA inputs in fp32, bf16 or fp16:
+    half-precision maps (autocast callers) are read as they are, without an fp32 round trip."""
     b, c, h, w = fmap1.shape
+    dt1, dt2 = _IN_DTYPES[fmap1.dtype], _IN_DTYPES[fmap2.dtype]
     lib = ofb200.load()
     st = ofb200.stream_ptr()
     dev = fmap1.device
@@ -52,10 +57,10 @@ def prepare_operands(fmap1: Tensor, fmap2: Tensor, num_levels: int):
     b_km = torch.empty((b, h * w, c), dtype=torch.bfloat16, device=dev)
     q_km = torch.empty((b, (h // 4) * (w // 4), c), dtype=torch.bfloat16, device=dev) if num_levels > 2 else None
     scale = 1.0 / math.sqrt(float(c))
-    ofb200.check(lib.ofb_corr_prep_bf16(ofb200.ptr(fmap1), ofb200.ptr(a_km), b, c, h, w, 1, scale, st), "ofb_corr_prep_bf16")
-    ofb200.check(lib.ofb_corr_prep_bf16(ofb200.ptr(fmap2), ofb200.ptr(b_km), b, c, h, w, 1, 1.0, st), "ofb_corr_prep_bf16")
+    ofb200.check(lib.ofb_corr_prep_from(ofb200.ptr(fmap1), dt1, ofb200.ptr(a_km), b, c, h, w, 1, scale, st), "ofb_corr_prep_from")
+    ofb200.check(lib.ofb_corr_prep_from(ofb200.ptr(fmap2), dt2, ofb200.ptr(b_km), b, c, h, w, 1, 1.0, st), "ofb_corr_prep_from")
     if q_km is not None:
-        ofb200.check(lib.ofb_corr_prep_bf16(ofb200.ptr(fmap2), ofb200.ptr(q_km), b, c, h, w, 4, 1.0, st), "ofb_corr_prep_bf16")
+        ofb200.check(lib.ofb_corr_prep_from(ofb200.ptr(fmap2), dt2, ofb200.ptr(q_km), b, c, h, w, 4, 1.0, st), "ofb_corr_prep_from")
     return a_km, b_km, q_km
 
 
@@ -236,8 +241,8 @@ class CorrBlock:
             diff_maps = (ofb200.to_device(fmap1), ofb200.to_device(fmap2))
         fmap1 = ofb200.to_device(fmap1).detach()
         fmap2 = ofb200.to_device(fmap2).detach()
-        if fmap1.dtype != torch.float32:
-            fmap1, fmap2 = fmap1.float(), fmap2.float()     # bf16 / fp16 feature maps (autocast callers)
+        if fmap1.dtype not in _IN_DTYPES or fmap2.dtype not in _IN_DTYPES:
+            raise NotImplementedError(f"CorrBlock: feature maps must be fp32, bf16 or fp16, got {fmap1.dtype} / {fmap2.dtype}")
         fmap1, fmap2 = fmap1.contiguous(), fmap2.contiguous()
         b, c, h, w = fmap1.shape
         if (h >> (num_levels - 1)) == 0 or (w >> (num_levels - 1)) == 0:
@@ -252,6 +257,9 @@ class CorrBlock:
         if builder == "tcgen05" and not tc_ok:
             raise NotImplementedError("CorrBlock: the tcgen05 builder needs a bf16 pyramid and C in {64,128,192,256}")
         self.builder = builder
+        if builder != "tcgen05" and fmap1.dtype != torch.float32:
+            fmap1, fmap2 = fmap1.float(), fmap2.float()     # the CUDA-core builder reads fp32; the tcgen05 prep reads
+                                                            # bf16 / fp16 maps (autocast callers) as they are
 
         pyr = ofb200.Pyramid()
         elems = (ctypes.c_int64 * ofb200.MAX_LEVELS)()
