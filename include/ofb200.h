@@ -212,7 +212,8 @@ int ofb_pyramid_layout(int h, int w, int levels, int mode, ofb_pyramid* pyr_host
  *         pyr->levels <= 2 (C multiple of 64, <= 256).  `scale` is applied to the accumulators
  *         (pass 1.0f when it was folded into fmap1).
  *         pyr: layout from ofb_pyramid_layout(padded = 1), dtype BF16.
- *         cta_group: 0 = auto, 1 = one CTA per tile, 2 = CTA pair (cta_group::2).
+ *         cta_group: 0 = auto, 1 = one CTA per tile, 2 = CTA pair (cta_group::2), 3 = clusters of two independent
+ *         cta_group::1 CTAs with the fmap2 operand ring TMA-multicast into both (query-minor layout only).
  * ofb_corr_pyramid_simt_f32: plain CUDA-core builder (fp32 in, fp32 or bf16 out) used by tests as an
  *         on-device cross-check and for shapes the tensor-core kernel rejects.
  * ------------------------------------------------------------------------------------- */

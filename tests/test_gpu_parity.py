@@ -1060,7 +1060,7 @@ def test_corr_pyramid_simt_golden(golden, builder, dtype):
     assert maxabs(N(out), g["odd_lookup"]) <= 1e-4
 
 
-@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("cta_group", [1, 2, 3])
 def test_corr_pyramid_tcgen05_golden(golden, cta_group):
     """tcgen05 builder on the golden 16x16 / C=64 case (single partial tile, pooled levels clipped)."""
     from model.corr import CorrBlock
@@ -1077,8 +1077,8 @@ def test_corr_pyramid_tcgen05_golden(golden, cta_group):
     assert np.linalg.norm(out - ref) / np.linalg.norm(ref) <= 6e-3
 
 
-@pytest.mark.parametrize("cta_group", [1, 2])
-@pytest.mark.parametrize("shape", [(2, 256, 47, 156), (1, 128, 55, 128), (1, 256, 40, 72), (3, 64, 9, 35)])
+@pytest.mark.parametrize("cta_group", [1, 2, 3])
+@pytest.mark.parametrize("shape", [(2, 256, 47, 156), (1, 128, 55, 128), (1, 256, 40, 72), (3, 64, 9, 35), (2, 256, 33, 50)])
 def test_corr_pyramid_tcgen05_vs_fp32(cta_group, shape):
     """Against the fp32 CUDA-core builder (reference op order) and, for the small case, the CPU oracle."""
     from model.corr import CorrBlock

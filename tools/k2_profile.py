@@ -15,7 +15,7 @@ from model.corr import CorrBlock, prepare_operands  # noqa: E402
 
 SHAPES = {"c3": (16, 256, 55, 128), "c4": (16, 256, 47, 156), "c5": (4, 256, 136, 240), "c5b8": (8, 256, 136, 240)}
 NAMES = ["tma_wait_b_empty", "tma_wait_a_empty", "mma_wait_a_full", "mma_wait_t_empty", "mma_wait_b_full",
-         "epi_wait_t_full", "epi_wait_store", "tiles", "kernel_cycles"]
+         "epi_wait_t_full", "epi_store_section", "tiles", "kernel_cycles", "epi_tmem_ld", "epi_bulk_wait"]
 
 
 def main():
@@ -28,7 +28,7 @@ def main():
         blk = CorrBlock(f1, f2)
         st = ofb200.stream_ptr()
         a_km, b_km, q_km = prepare_operands(f1, f2, 4)
-        for cg in (1, 2):
+        for cg in tuple(int(x) for x in os.environ.get("K2_PROF_CG", "1,2").split(",")):
             prof = torch.zeros((2, 148, 16), dtype=torch.int64, device="cuda")
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             for it in range(2):
@@ -42,7 +42,8 @@ def main():
             p1 = prof[1].cpu().double()
             p = prof[0].cpu().double()                 # slot 0 = the full-resolution run (levels 0, 1)
             p = p[p[:, 8] > 0]
-            rec = {"shape": key, "cta_group": cg, "dbg": os.environ.get("OFB_K2_DBG", "0"), "ctas": int(p.shape[0])}
+            rec = {"shape": key, "cta_group": cg, "dbg": os.environ.get("OFB_K2_DBG", "0"), "ctas": int(p.shape[0]),
+                   "epi": os.environ.get("OFB_K2_EPI", "default")}
             for i, nm in enumerate(NAMES):
                 rec[nm] = round(float(p[:, i].mean()), 1)
             rec["ms_both_runs"] = round(e0.elapsed_time(e1), 4)
@@ -51,8 +52,10 @@ def main():
             rec["mhz_if_serial"] = round((rec["run1_kernel_cycles_max"] + rec["run2_kernel_cycles_max"]) / rec["ms_both_runs"] / 1e3, 1)
             t = max(rec["tiles"], 1.0)
             rec["cycles_per_tile"] = round(rec["kernel_cycles"] / t, 1)
-            for nm in NAMES[:7]:
+            for nm in NAMES[:7] + NAMES[9:]:
                 rec[nm + "_per_tile"] = round(rec[nm] / t, 1)
+            for nm in NAMES:
+                rec.pop(nm, None)
             print(json.dumps(rec), flush=True)
         del blk
 

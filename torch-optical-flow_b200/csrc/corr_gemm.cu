@@ -63,18 +63,33 @@ constexpr int OFF_A = 0;
 constexpr int OFF_B = OFF_A + MAX_KB * A_KB_BYTES;         // 64 KiB, 1024-aligned
 // The query-minor layout needs no epilogue staging (direct register stores): its shared memory goes to a deeper
 // operand ring instead (the stream is latency-bound: 2 / 3 stages of 32 KiB measured 6900 / 5000 cycles per tile).
-template <int CG, int LAY> struct Ring {
+// Epilogue store modes of the query-minor layout:
+//   EPI_DIRECT  32-byte register stores (st.global.v8.b32), no staging: the whole budget goes to a 5-stage operand ring;
+//   EPI_BULK    each warp stages one 8x4 block of its 32 queries -- 2 KiB that are CONTIGUOUS in the query-minor layout --
+//               in shared memory and hands it to the TMA engine (cp.async.bulk.global.shared::cta): full-line writes that
+//               never pass through the LSU, and the warp does not wait for them (round-2 probes).
+//   EPI_PIPE    EPI_DIRECT's stores, software-pipelined: the accumulator leaves TMEM in 32-column pieces (two block rows of
+//               two blocks = exactly two 32-byte sector stores per lane), and the tcgen05.ld of piece p+1 -- across tile
+//               boundaries too -- is in flight while piece p is converted and stored.  Measured (profiles/r02_k2_ablate*):
+//               with 8 warps sharing the TMEM read port a 64-column tcgen05.ld stalls its warp for ~850 cycles, and in
+//               EPI_DIRECT that stall and the ~1170 cycles of store issue per chunk are serial.
+constexpr int EPI_DIRECT = 0, EPI_BULK = 1, EPI_PIPE = 2;
+constexpr int BULK_BLOCK_BYTES = 32 * 64;                      // 32 queries x one 64-byte block slot
+constexpr int BULK_WARP_BYTES = 2 * BULK_BLOCK_BYTES;          // X: the level-0 block in flight, Y: the warp's level-1 block
+template <int CG, int LAY, int EPI = EPI_DIRECT> struct Ring {
     static constexpr bool STAGED = LAY != OFB_LAYOUT_QMINOR8X4;
+    static constexpr bool BULK = !STAGED && EPI == EPI_BULK;
     static constexpr int STAGE_BYTES = B_TILE_KB_BYTES / CG;              // 32 KiB / 16 KiB
-    static constexpr int STAGES = (STAGED ? 3 : 5) * CG;                  // 96 KiB, or 160 KiB without the staging area
+    static constexpr int STAGES = (STAGED ? 3 : BULK ? 4 : 5) * CG;       // 96 / 128 / 160 KiB
     static constexpr int OFF_STG = OFF_B + STAGES * STAGE_BYTES;
-    static constexpr int OFF_BAR = OFF_STG + (STAGED ? NUM_EPI_WARPS * STG_WARP_BYTES : 0);
+    static constexpr int OFF_BAR = OFF_STG + (STAGED ? NUM_EPI_WARPS * STG_WARP_BYTES : BULK ? NUM_EPI_WARPS * BULK_WARP_BYTES : 0);
     static constexpr int NUM_BARS = 2 + 2 * MAX_STAGES + 4;                // a_full, a_empty, b_full[], b_empty[], t_full[2], t_empty[2]
     static constexpr int SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16;
     static constexpr int SMEM_ALLOC = SMEM_BYTES + 1024;                   // manual 1024-byte alignment of the dynamic segment
 };
 static_assert(Ring<1, 0>::SMEM_ALLOC <= 232448 && Ring<2, 0>::SMEM_ALLOC <= 232448 && Ring<1, 2>::SMEM_ALLOC <= 232448 &&
-              Ring<2, 2>::SMEM_ALLOC <= 232448 && Ring<2, 2>::STAGES <= MAX_STAGES, "shared memory budget");
+              Ring<2, 2>::SMEM_ALLOC <= 232448 && Ring<2, 2>::STAGES <= MAX_STAGES && Ring<1, 2, 1>::SMEM_ALLOC <= 232448 &&
+              Ring<2, 2, 1>::SMEM_ALLOC <= 232448, "shared memory budget");
 
 struct LevelOut {
     __nv_bfloat16* base;
@@ -200,6 +215,15 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
             "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
             ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol) : "memory");
 }
+// The same box delivered to the SAME CTA-relative offset (data and mbarrier) of every CTA in `mask`: one L2 read
+// feeds both CTAs of a cluster.
+__device__ __forceinline__ void tma_load_4d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                               int c3, uint16_t mask, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint "
+        "[%0], [%1, {%3, %4, %5, %6}], [%2], %7, %8;"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
 }
@@ -243,6 +267,12 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
             "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
             ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
+// cta_group::1 MMAs retiring -> one arrival on the barrier at this offset in BOTH CTAs of the cluster
+__device__ __forceinline__ void umma_commit_both(uint32_t bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
 // 32 lanes x 64 consecutive fp32 columns
 __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[64]) {
     asm volatile(
@@ -259,6 +289,18 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[64]) {
           "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]),
           "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]),
           "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+        : "r"(taddr) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -301,6 +343,39 @@ __device__ __forceinline__ void st_global_v8(void* p, const uint32_t* a, const u
                  ::"l"(p), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]) : "memory");
 }
 
+// TMA bulk store of a contiguous run, shared -> global; completion is tracked per issuing thread in bulk async-groups
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all of this thread's bulk stores have finished READING shared memory (the staging buffer may be rewritten)
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy writes (st.shared) -> visible to the async proxy (the TMA engine)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// One 64-byte block slot per lane -> the warp's staging buffer, conflict-free: the four 16-byte pieces (block rows) of a
+// lane are stored in the order (i + rot) & 3 with rot = (lane >> 1) & 3, so the 8 lanes of a store phase hit 8 different
+// 16-byte bank groups although their slots are 64 bytes apart.  The register file cannot be indexed dynamically: the
+// pieces are rotated by `rot` with two select stages first.  p0..p3 = the lane's pieces in memory order.
+__device__ __forceinline__ void stage_slot(uint32_t slot, uint32_t rot, const uint32_t* p0, const uint32_t* p1,
+                                           const uint32_t* p2, const uint32_t* p3) {
+    const bool r1 = rot & 1u, r2 = rot & 2u;
+    uint32_t a[4][4], b[4][4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        a[0][e] = r1 ? p1[e] : p0[e]; a[1][e] = r1 ? p2[e] : p1[e];
+        a[2][e] = r1 ? p3[e] : p2[e]; a[3][e] = r1 ? p0[e] : p3[e];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) b[i][e] = r2 ? a[(i + 2) & 3][e] : a[i][e];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        st_shared_v4(slot + ((((uint32_t)i + rot) & 3u) << 4), b[i][0], b[i][1], b[i][2], b[i][3]);
+}
+
 struct ItemCoord {
     int b, chunk, m;
 };
@@ -313,13 +388,81 @@ __device__ __forceinline__ ItemCoord decode_item(const GemmParams& P, int item) 
     return ic;
 }
 
+// The (item, tile) sequence of one worker, as the three roles walk it.
+struct TileIter {
+    int item, t, t1;
+    ItemCoord ic;
+    bool valid;
+    __device__ __forceinline__ void load(const GemmParams& P) {
+        valid = item < P.n_items;
+        if (valid) {
+            ic = decode_item(P, item);
+            t = ic.chunk * P.tiles_per_item;
+            t1 = min(t + P.tiles_per_item, P.ntiles);
+        }
+    }
+    __device__ __forceinline__ void init(const GemmParams& P, int worker) { item = worker; load(P); }
+    __device__ __forceinline__ void advance(const GemmParams& P, int n_workers) {
+        if (++t >= t1) { item += n_workers; load(P); }
+    }
+};
+
+// EPI_PIPE: one 32-column piece = block rows 2*rh, 2*rh+1 of the chunk's two 8x4 blocks (chunk = 16 x 4 targets, column
+// c = row * 16 + x).  Level 0: one 32-byte sector per block.  Level 1: the piece closes ONE pooled row (8 means); the
+// even piece keeps it in `keep`, the odd piece stores both rows as one sector.
+__device__ __forceinline__ void store_piece(const GemmParams& P, const uint32_t (&v)[32], int rh, int x0, int y0,
+                                            long long qg, bool qok, uint32_t (&keep)[4]) {
+    float f[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) f[c] = P.apply_scale ? __uint_as_float(v[c]) * P.scale : __uint_as_float(v[c]);
+    if (qok && y0 < P.la.h) {
+#pragma unroll
+        for (int b2 = 0; b2 < 2; ++b2) {
+            const int x = x0 + b2 * 8;
+            if (x < P.la.pitch) {
+                uint32_t r0[4], r1[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    r0[e] = pack_bf16(f[b2 * 8 + 2 * e], f[b2 * 8 + 2 * e + 1]);
+                    r1[e] = pack_bf16(f[16 + b2 * 8 + 2 * e], f[16 + b2 * 8 + 2 * e + 1]);
+                }
+                st_global_v8(P.la.base + qg * P.la.q_stride + piece_offset(P.la, y0, x) + rh * 16, r0, r1);
+            }
+        }
+    }
+    if (P.has_b) {
+        uint32_t mk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {       // 2x2 means, summed in the reference's raster order then / 4 (corr.py:53)
+            const int a0 = 4 * e, a1 = 4 * e + 2;
+            const float m0 = (((f[a0] + f[a0 + 1]) + f[a0 + 16]) + f[a0 + 17]) * 0.25f;
+            const float m1 = (((f[a1] + f[a1 + 1]) + f[a1 + 16]) + f[a1 + 17]) * 0.25f;
+            mk[e] = pack_bf16(m0, m1);
+        }
+        if (rh == 0) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) keep[e] = mk[e];
+        } else {
+            const int y = y0 >> 1, x = x0 >> 1;
+            if (qok && y < P.lb.h && x < P.lb.pitch)
+                st_global_v8(P.lb.base + qg * P.lb.q_stride + piece_offset(P.lb, y, x), keep, mk);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------ the kernel
 // LAY: output layout (OFB_LAYOUT_ROWS / BLOCK8X4 / QMINOR8X4)
-template <int CG, bool PROF, int LAY>
+// MC (CG == 1 only): CTAs run as CLUSTERS OF TWO that walk the same target tiles with their own 128 queries each, their own
+// accumulators and their own cta_group::1 MMAs; every fmap2 stage is fetched half by each CTA and MULTICAST into both, so
+// the L2 -> SM operand stream is halved (as with cta_group::2) while the two epilogues stay independent.
+template <int CG, bool PROF, int LAY, int EPI, bool MC>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const GemmParams P) {
-    using R = Ring<CG, LAY>;
+    static_assert(!MC || CG == 1, "multicast clusters issue cta_group::1 MMAs");
+    using R = Ring<CG, LAY, EPI>;
+    constexpr bool BULK = R::BULK;
+    constexpr int CL = (CG == 2 || MC) ? 2 : 1;                  // CTAs per cluster
     constexpr bool BLK = LAY != OFB_LAYOUT_ROWS;
     extern __shared__ uint8_t smem_raw[];
     // the 128-byte swizzle is a function of the absolute shared address: align the segment to 1024
@@ -337,15 +480,16 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sgen + R::OFF_BAR + R::NUM_BARS * 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const uint32_t rank = (CL == 2) ? cluster_ctarank() : 0u;
     const bool leader = rank == 0;
-    const int worker = blockIdx.x / CG, n_workers = gridDim.x / CG;
+    const int worker = blockIdx.x / CL, n_workers = gridDim.x / CL;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&map_a); prefetch_tmap(&map_b);
         mbar_init(bar_a_full, 1);
         mbar_init(bar_a_empty, 1);
-        for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(bar_b_full + 8 * s, 1); mbar_init(bar_b_empty + 8 * s, 1); }
+        // multicast: a stage is written in BOTH CTAs by either producer, so it is free when both MMA lanes are done with it
+        for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(bar_b_full + 8 * s, 1); mbar_init(bar_b_empty + 8 * s, MC ? 2 : 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(bar_t_full + 8 * s, 1); mbar_init(bar_t_empty + 8 * s, NUM_EPI_WARPS * CG); }
         fence_barrier_init();
     }
@@ -354,14 +498,15 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         tmem_relinquish<CG>();
     }
     tc_fence_before();
-    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    if (CL == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
 
-    const int m_rows = BLOCK_M * CG;   // query rows per work item
+    const int m_rows = BLOCK_M * CL;   // query rows per work item
     const long long t_start = PROF ? clock64() : 0;
     const int dbg = PROF ? P.dbg : 0;
     unsigned long long pw0 = 0, pw1 = 0, pw2 = 0, ptiles = 0;   // per-role wait cycles (PROF only)
+    unsigned long long p_ld = 0, p_st = 0, p_bw = 0;            // epilogue: tcgen05.ld + wait, store section, bulk-wait
 
     if (warp == 0) {
         // ============================== TMA producer (one lane) ==============================
@@ -369,8 +514,8 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const uint32_t full_a = (CG == 2) ? map_to_rank(bar_a_full, 0) : bar_a_full;
             // which part of the tile this CTA fetches (cta_group 2: chunks {2*rank, 2*rank+1})
             const int TH = P.CR * P.YQ;
-            const int xb0 = (CG == 2 && P.XB >= 2) ? (int)rank * (P.XB / 2) : 0;
-            const int yoff = (CG == 2 && P.XB == 1) ? (int)rank * (TH / 2) : 0;
+            const int xb0 = (CL == 2 && P.XB >= 2) ? (int)rank * (P.XB / 2) : 0;
+            const int yoff = (CL == 2 && P.XB == 1) ? (int)rank * (TH / 2) : 0;
             const int box_bytes = P.CW * P.box_rows * 128;
             const uint64_t pol = l2_policy_evict_last();
             uint32_t stage = 0, bphase = 0, aphase = 0;
@@ -378,7 +523,7 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 const ItemCoord ic = decode_item(P, item);
                 mbar_wait_p<PROF>(bar_a_empty, aphase ^ 1, pw1);
                 aphase ^= 1;
-                if (leader) mbar_expect_tx(bar_a_full, (uint32_t)(P.kb * A_KB_BYTES * CG));
+                if (leader || MC) mbar_expect_tx(bar_a_full, (uint32_t)(P.kb * A_KB_BYTES * CG));
                 const int row0 = ic.m * m_rows + (int)rank * BLOCK_M;
                 for (int kb = 0; kb < P.kb; ++kb)
                     tma_load_3d<CG>(sbase + OFF_A + kb * A_KB_BYTES, &map_a, full_a, kb * BLOCK_K, row0, ic.b, pol);
@@ -390,10 +535,13 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     for (int kb = 0; kb < P.kb; ++kb) {
                         mbar_wait_p<PROF>(bar_b_empty + 8 * stage, bphase ^ 1, pw0);
                         const uint32_t full_b = (CG == 2) ? map_to_rank(bar_b_full + 8 * stage, 0) : bar_b_full + 8 * stage;
-                        if (leader) mbar_expect_tx(bar_b_full + 8 * stage, (uint32_t)B_TILE_KB_BYTES);
-                        const uint32_t dst = sbase + OFF_B + stage * B_STAGE_BYTES;
-                        for (int j = 0; j < P.nbox; ++j)
-                            tma_load_4d<CG>(dst + j * box_bytes, &map_b, full_b, kb * BLOCK_K, x0 + P.CW * j, y0, ic.b, pol);
+                        if (leader || MC) mbar_expect_tx(bar_b_full + 8 * stage, (uint32_t)B_TILE_KB_BYTES);
+                        // multicast: this CTA's half of the tile goes to the same place in both CTAs
+                        const uint32_t dst = sbase + OFF_B + stage * B_STAGE_BYTES + (MC ? rank * (uint32_t)(B_TILE_KB_BYTES / 2) : 0u);
+                        for (int j = 0; j < P.nbox; ++j) {
+                            if (MC) tma_load_4d_mc(dst + j * box_bytes, &map_b, full_b, kb * BLOCK_K, x0 + P.CW * j, y0, ic.b, (uint16_t)3, pol);
+                            else tma_load_4d<CG>(dst + j * box_bytes, &map_b, full_b, kb * BLOCK_K, x0 + P.CW * j, y0, ic.b, pol);
+                        }
                         if (++stage == B_STAGES) { stage = 0; bphase ^= 1; }
                     }
                 }
@@ -406,7 +554,7 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         __syncwarp();
     } else if (warp == 1) {
         // ============================== MMA issuer (leader CTA, one lane) ====================
-        if (leader && lane == 0) {
+        if ((leader || MC) && lane == 0) {
             constexpr uint32_t idesc = make_idesc(BLOCK_M * CG, TILE_N);
             uint32_t stage = 0, bphase = 0, aphase = 0, acc = 0, tphase = 0;
             for (int item = worker; item < P.n_items; item += n_workers) {
@@ -431,7 +579,8 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                             umma_bf16<CG>(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
                                           (uint32_t)((kb | k) != 0));
                         }
-                        umma_commit<CG>(bar_b_empty + 8 * stage);      // smem stage free once these MMAs retire
+                        if (MC) umma_commit_both(bar_b_empty + 8 * stage);   // both CTAs' producers may refill it
+                        else umma_commit<CG>(bar_b_empty + 8 * stage); // smem stage free once these MMAs retire
                         if (++stage == B_STAGES) { stage = 0; bphase ^= 1; }
                     }
                     umma_commit<CG>(bar_t_full + 8 * acc);             // accumulator ready for the epilogue
@@ -445,6 +594,68 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
         }
         __syncwarp();
+    } else if (EPI == EPI_PIPE && LAY == OFB_LAYOUT_QMINOR8X4) {
+        // ============================== epilogue, software-pipelined (8 warps) ===============
+        const int q4 = warp & 3, half = (warp - 2) >> 2;
+        uint32_t acc = 0, tphase = 0;
+        TileIter it;
+        it.init(P, worker);
+        if (it.valid) {
+            uint32_t buf0[32], buf1[32], keep[4] = {0, 0, 0, 0};
+            const uint32_t tlane = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)half * 2 * CHUNK;
+            mbar_wait_p<PROF>(bar_t_full + 8 * acc, tphase, pw0);
+            tc_fence_after();
+            uint32_t taddr = tlane + acc * TILE_N;
+            tmem_ld32(taddr, buf0);
+            while (true) {
+                if (PROF) ++ptiles;
+                const int ty = it.t / P.ntx, tx = it.t - ty * P.ntx;
+                const int qrow = it.ic.m * m_rows + (int)rank * BLOCK_M + q4 * 32 + lane;     // this lane's query row
+                const bool qok = qrow < P.Nq;
+                const long long qg = (long long)it.ic.b * P.Nq + qrow;
+                TileIter nxt = it;
+                nxt.advance(P, n_workers);
+                uint32_t taddr_next = 0;
+#pragma unroll
+                for (int pc = 0; pc < 4; ++pc) {
+                    tmem_ld_wait();                                   // piece pc has landed (the only load in flight)
+                    if (pc < 3) {
+                        if ((pc & 1) == 0) tmem_ld32(taddr + (pc + 1) * 32, buf1);
+                        else tmem_ld32(taddr + (pc + 1) * 32, buf0);
+                    } else {
+                        // all four pieces of this warp have left TMEM: hand the accumulator stage back ...
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (CG == 2) mbar_arrive_cluster(bar_t_empty + 8 * acc, 0);
+                            else mbar_arrive_local(bar_t_empty + 8 * acc);
+                        }
+                        if (++acc == 2) { acc = 0; tphase ^= 1; }
+                        // ... and fetch the first piece of the next tile before this tile's last stores are issued
+                        if (nxt.valid) {
+                            mbar_wait_p<PROF>(bar_t_full + 8 * acc, tphase, pw0);
+                            tc_fence_after();
+                            taddr_next = tlane + acc * TILE_N;
+                            tmem_ld32(taddr_next, buf0);
+                        }
+                    }
+                    const int k = half * 2 + (pc >> 1);
+                    const int xb = k / P.YQ, yq = k - xb * P.YQ;
+                    const int x0 = (tx * P.XB + xb) * P.CW, y0 = (ty * P.YQ + yq) * P.CR;
+                    if (!(PROF && (dbg & 1))) {
+                        if ((pc & 1) == 0) store_piece(P, buf0, 0, x0, y0, qg, qok, keep);
+                        else store_piece(P, buf1, 1, x0, y0, qg, qok, keep);
+                    }
+                }
+                if (!nxt.valid) break;
+                it = nxt;
+                taddr = taddr_next;
+            }
+        }
+        if (PROF && P.prof && warp == 2 && lane == 0) {
+            unsigned long long* o = P.prof + (size_t)blockIdx.x * 16;
+            o[5] = pw0; o[6] = 0; o[7] = ptiles; o[8] = (unsigned long long)(clock64() - t_start);
+        }
     } else {
         // ============================== epilogue (8 warps) ===================================
         // warp -> TMEM lane quarter (hardware rule: warp_id % 4) and column half; thread -> one query row
@@ -467,6 +678,11 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int qm_q = lane >> 2, qm_s = lane & 3;
         // level B -- 2 lanes per query, 16 queries per instruction
         const int rb_q = lane >> 1, rb_p = lane & 1;
+        // bulk-store staging (EPI_BULK): X = the level-0 block in flight, Y = the level-1 block of the tile
+        const uint32_t xbuf = sbase + R::OFF_STG + (uint32_t)(warp - 2) * BULK_WARP_BYTES, ybuf = xbuf + BULK_BLOCK_BYTES;
+        const uint32_t rot = (uint32_t)(lane >> 1) & 3u;
+        const bool bulk_b = P.YQ == 2;          // the warp's two chunks stack vertically: they close one level-1 block
+        uint32_t mk_top[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         uint32_t acc = 0, tphase = 0;
         for (int item = worker; item < P.n_items; item += n_workers) {
             const ItemCoord ic = decode_item(P, item);
@@ -488,8 +704,10 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
                         for (int c = 0; c < 64; ++c) v[c] = 0x3f800000u + c;
                     } else {
+                        const long long tl0 = PROF ? clock64() : 0;
                         tmem_ld64(taddr + cc * CHUNK, v);
                         tmem_ld_wait();
+                        if (PROF) p_ld += (unsigned long long)(clock64() - tl0);
                     }
                     if (cc == 1) {
                         // both chunks of this warp have left TMEM: hand the accumulator stage back
@@ -509,22 +727,40 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         for (int c = 0; c < 64; ++c) f[c] = __uint_as_float(v[c]);
                     }
                     if (qminor && !(PROF && (dbg & 64))) {
-                        // ---- query-minor blocks: a lane's two 64-byte block slots are its own, and the 32 lanes'
-                        // slots are adjacent -- store straight from registers, one full 32-byte sector (two block rows)
-                        // per lane and instruction; no shared-memory transpose, no barriers
+                        // ---- query-minor blocks: a lane's 64-byte block slots are its own and the 32 lanes' slots are
+                        // adjacent, so one block of the warp's 32 queries is a contiguous 2 KiB run
                         const int xb = k / P.YQ, yq = k - xb * P.YQ;
                         const int x0 = (tx * P.XB + xb) * P.CW, y0 = (ty * P.YQ + yq) * P.CR;
                         uint32_t pk[32];
 #pragma unroll
                         for (int c = 0; c < 32; ++c) pk[c] = pack_bf16(f[2 * c], f[2 * c + 1]);
                         const bool qok = qrow0 + lane < P.Nq;
+                        const int nvalid = min(32, P.Nq - qrow0);          // queries of this warp inside the batch element
+                        const long long ts0 = PROF ? clock64() : 0;
                         if (!(PROF && (dbg & 1))) {
 #pragma unroll
                             for (int b2 = 0; b2 < 2; ++b2) {
                                 const int x = x0 + b2 * 8;
-                                if (qok && y0 < P.la.h && x < P.la.pitch) {
+                                // register piece (block row yy, block b2) = pk[4 * (2 * yy + b2) ..]
+                                if (BULK) {
+                                    if (nvalid > 0 && y0 < P.la.h && x < P.la.pitch) {      // warp-uniform
+                                        const long long tb0 = PROF ? clock64() : 0;
+                                        if (lane == 0) bulk_wait_read_all();               // the previous block has left X
+                                        __syncwarp();
+                                        if (PROF) p_bw += (unsigned long long)(clock64() - tb0);
+                                        stage_slot(xbuf + (uint32_t)lane * 64u, rot, pk + 4 * b2, pk + 4 * (2 + b2),
+                                                   pk + 4 * (4 + b2), pk + 4 * (6 + b2));
+                                        fence_async_smem();
+                                        __syncwarp();
+                                        if (lane == 0) {
+                                            bulk_store(P.la.base + qglob0 * P.la.q_stride + piece_offset(P.la, y0, x), xbuf,
+                                                       (uint32_t)nvalid * 64u);
+                                            bulk_commit();
+                                        }
+                                    }
+                                } else if (qok && y0 < P.la.h && x < P.la.pitch) {
+                                    // direct: one full 32-byte sector (two block rows) per lane and instruction
                                     __nv_bfloat16* dst = P.la.base + (qglob0 + lane) * P.la.q_stride + piece_offset(P.la, y0, x);
-                                    // register piece (block row yy, block b2) = pk[4 * (2 * yy + b2) ..]
                                     st_global_v8(dst, pk + 4 * b2, pk + 4 * (2 + b2));
                                     st_global_v8(dst + 16, pk + 4 * (4 + b2), pk + 4 * (6 + b2));
                                 }
@@ -540,9 +776,28 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                                 mk[c] = pack_bf16(m0, m1);
                             }
                             const int y = y0 >> 1, x = x0 >> 1;
-                            if (qok && y < P.lb.h && x < P.lb.pitch)
+                            if (BULK && bulk_b) {
+                                // 2 x 2 chunks per tile: this warp's two chunks are rows 0-1 and rows 2-3 of ONE level-1 block
+                                if (cc == 0) {
+#pragma unroll
+                                    for (int c = 0; c < 8; ++c) mk_top[c] = mk[c];
+                                } else if (nvalid > 0 && (y & ~3) < P.lb.h && x < P.lb.pitch) {
+                                    if (lane == 0) bulk_wait_read_all();
+                                    __syncwarp();
+                                    stage_slot(ybuf + (uint32_t)lane * 64u, rot, mk_top, mk_top + 4, mk, mk + 4);
+                                    fence_async_smem();
+                                    __syncwarp();
+                                    if (lane == 0) {
+                                        bulk_store(P.lb.base + qglob0 * P.lb.q_stride + piece_offset(P.lb, y & ~3, x), ybuf,
+                                                   (uint32_t)nvalid * 64u);
+                                        bulk_commit();
+                                    }
+                                }
+                            } else if (qok && y < P.lb.h && x < P.lb.pitch) {
                                 st_global_v8(P.lb.base + (qglob0 + lane) * P.lb.q_stride + piece_offset(P.lb, y, x), mk, mk + 4);
+                            }
                         }
+                        if (PROF) p_st += (unsigned long long)(clock64() - ts0);
                         continue;
                     }
                     // ---- registers -> swizzled stage.  chunk = 2 image rows x 32 columns, piece p = 8 bf16
@@ -630,15 +885,17 @@ corr_pyramid_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 if (++acc == 2) { acc = 0; tphase ^= 1; }
             }
         }
+        if (BULK && lane == 0) bulk_wait_all();          // the staging memory and the stores outlive the loop
         if (PROF && P.prof && warp == 2 && lane == 0) {
             unsigned long long* o = P.prof + (size_t)blockIdx.x * 16;
-            o[5] = pw0; o[6] = 0; o[7] = ptiles; o[8] = (unsigned long long)(clock64() - t_start);
+            o[5] = pw0; o[6] = p_st; o[7] = ptiles; o[8] = (unsigned long long)(clock64() - t_start);
+            o[9] = p_ld; o[10] = p_bw;
         }
     }
 
     // teardown: nobody may leave (or free TMEM) while a peer can still signal / read this CTA
     tc_fence_before();
-    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    if (CL == 2) cluster_sync_all(); else __syncthreads();
     if (warp == 1) tmem_dealloc<CG>(tmem_base, TMEM_COLS);
 }
 
@@ -672,28 +929,28 @@ bool encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims
     return r == CUDA_SUCCESS;
 }
 
-template <int CG, bool PROF, int LAY>
+template <int CG, bool PROF, int LAY, int EPI, bool MC>
 int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& P, int grid, cudaStream_t st) {
     static bool configured[OFB_MAX_DEVICES] = {false};
     const int dev = ofb_device();
     if (!configured[dev]) {
-        OFB_CUDA(cudaFuncSetAttribute(corr_pyramid_kernel<CG, PROF, LAY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      Ring<CG, LAY>::SMEM_ALLOC));
+        OFB_CUDA(cudaFuncSetAttribute(corr_pyramid_kernel<CG, PROF, LAY, EPI, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      Ring<CG, LAY, EPI>::SMEM_ALLOC));
         configured[dev] = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = Ring<CG, LAY>::SMEM_ALLOC;
+    cfg.dynamicSmemBytes = Ring<CG, LAY, EPI>::SMEM_ALLOC;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.x = (CG == 2 || MC) ? 2 : 1;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    OFB_CUDA(cudaLaunchKernelEx(&cfg, corr_pyramid_kernel<CG, PROF, LAY>, ma, mb, P));
+    OFB_CUDA(cudaLaunchKernelEx(&cfg, corr_pyramid_kernel<CG, PROF, LAY, EPI, MC>, ma, mb, P));
     OFB_LAUNCH_CHECK();
     return OFB_OK;
 }
@@ -701,7 +958,12 @@ int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& 
 // One GEMM run: queries (B, Nq, C) x targets (B, th*tw, C) -> level la_idx (th x tw per query) and, when
 // lb_idx >= 0, its 2x2 mean.
 int run_gemm(const void* f1_km, const void* f2_km, const ofb_pyramid* pyr, int la_idx, int lb_idx, int B, int C, int Nq,
-             int th, int tw, float scale, int cg, unsigned long long* prof, int prof_slot, cudaStream_t st) {
+             int th, int tw, float scale, int cg_mode, unsigned long long* prof, int prof_slot, cudaStream_t st) {
+    // cg_mode: 1 = one CTA per tile, 2 = CTA pair sharing one 256-row accumulator tile (cta_group::2),
+    //          3 = cluster of two independent cta_group::1 CTAs with the fmap2 ring multicast into both
+    const bool mc = cg_mode == 3;
+    const int cg = mc ? 1 : cg_mode;           // tcgen05 cta_group
+    const int cl = (cg == 2 || mc) ? 2 : 1;    // CTAs per cluster / work item
     GemmParams P = {};
     P.B = B; P.C = C; P.kb = C / BLOCK_K; P.Nq = Nq; P.th = th; P.tw = tw;
     P.scale = scale; P.apply_scale = (scale != 1.0f) ? 1 : 0;
@@ -724,10 +986,10 @@ int run_gemm(const void* f1_km, const void* f2_km, const ofb_pyramid* pyr, int l
     }
     const int TW = P.CW * P.XB, TH = P.CR * P.YQ;
     P.ntx = (tw + TW - 1) / TW; P.nty = (th + TH - 1) / TH; P.ntiles = P.ntx * P.nty;
-    if (cg == 2) { P.nbox = P.XB >= 2 ? P.XB / 2 : 1; P.box_rows = P.XB == 1 ? TH / 2 : TH; }
+    if (cl == 2) { P.nbox = P.XB >= 2 ? P.XB / 2 : 1; P.box_rows = P.XB == 1 ? TH / 2 : TH; }
     else { P.nbox = P.XB; P.box_rows = TH; }
-    P.mblk = (Nq + BLOCK_M * cg - 1) / (BLOCK_M * cg);
-    const int workers = ofb_num_sms() / cg;
+    P.mblk = (Nq + BLOCK_M * cl - 1) / (BLOCK_M * cl);
+    const int workers = ofb_num_sms() / cl;
     // split the target tiles of one (batch, query block) into chunks so the last wave is not mostly idle:
     // pick the chunk count (<= 8) that minimises ceil(items / workers) * tiles_per_item
     int best_chunks = 1;
@@ -774,14 +1036,30 @@ int run_gemm(const void* f1_km, const void* f2_km, const ofb_pyramid* pyr, int l
         const uint32_t box[4] = {BLOCK_K, (uint32_t)P.CW, (uint32_t)P.box_rows, 1};
         if (!encode_map(&mb, f2_km, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B)) return OFB_EDRIVER;
     }
-    int grid = workers * cg;
-    if ((long long)grid > n_items * cg) grid = (int)(n_items * cg);
-#define OFB_GEMM_CASE(CGV, PROFV, LAYV) \
-    if (cg == CGV && (prof != nullptr) == PROFV && pyr->layout == LAYV) return launch_gemm<CGV, PROFV, LAYV>(ma, mb, P, grid, st);
-    OFB_GEMM_CASE(1, false, 0) OFB_GEMM_CASE(1, false, 1) OFB_GEMM_CASE(1, false, 2)
-    OFB_GEMM_CASE(2, false, 0) OFB_GEMM_CASE(2, false, 1) OFB_GEMM_CASE(2, false, 2)
-    OFB_GEMM_CASE(1, true, 0) OFB_GEMM_CASE(1, true, 1) OFB_GEMM_CASE(1, true, 2)
-    OFB_GEMM_CASE(2, true, 0) OFB_GEMM_CASE(2, true, 1) OFB_GEMM_CASE(2, true, 2)
+    int grid = workers * cl;
+    if ((long long)grid > n_items * cl) grid = (int)(n_items * cl);
+    // epilogue store mode of the query-minor layout (OFB_K2_EPI=direct|bulk overrides; other layouts stage through smem)
+    int epi = EPI_DIRECT;
+    if (const char* e = getenv("OFB_K2_EPI")) epi = (e[0] == 'd' || e[0] == '0') ? EPI_DIRECT : (e[0] == 'p' || e[0] == '2') ? EPI_PIPE : EPI_BULK;
+    if (pyr->layout != OFB_LAYOUT_QMINOR8X4) epi = EPI_DIRECT;
+#define OFB_GEMM_CASE(CGV, PROFV, LAYV, EPIV) \
+    if (cg == CGV && !mc && (prof != nullptr) == PROFV && pyr->layout == LAYV && epi == EPIV) \
+        return launch_gemm<CGV, PROFV, LAYV, EPIV, false>(ma, mb, P, grid, st);
+    OFB_GEMM_CASE(1, false, 0, 0) OFB_GEMM_CASE(1, false, 1, 0) OFB_GEMM_CASE(1, false, 2, 0) OFB_GEMM_CASE(1, false, 2, 1)
+    OFB_GEMM_CASE(2, false, 0, 0) OFB_GEMM_CASE(2, false, 1, 0) OFB_GEMM_CASE(2, false, 2, 0) OFB_GEMM_CASE(2, false, 2, 1)
+    OFB_GEMM_CASE(1, true, 0, 0) OFB_GEMM_CASE(1, true, 1, 0) OFB_GEMM_CASE(1, true, 2, 0) OFB_GEMM_CASE(1, true, 2, 1)
+    OFB_GEMM_CASE(2, true, 0, 0) OFB_GEMM_CASE(2, true, 1, 0) OFB_GEMM_CASE(2, true, 2, 0) OFB_GEMM_CASE(2, true, 2, 1)
+    OFB_GEMM_CASE(1, false, 2, 2) OFB_GEMM_CASE(2, false, 2, 2) OFB_GEMM_CASE(1, true, 2, 2) OFB_GEMM_CASE(2, true, 2, 2)
+    // multicast clusters: the product layout (query-minor) only
+    if (mc && pyr->layout == OFB_LAYOUT_QMINOR8X4) {
+        if (!prof && epi == EPI_DIRECT) return launch_gemm<1, false, 2, 0, true>(ma, mb, P, grid, st);
+        if (!prof && epi == EPI_BULK) return launch_gemm<1, false, 2, 1, true>(ma, mb, P, grid, st);
+        if (prof && epi == EPI_DIRECT) return launch_gemm<1, true, 2, 0, true>(ma, mb, P, grid, st);
+        if (prof && epi == EPI_BULK) return launch_gemm<1, true, 2, 1, true>(ma, mb, P, grid, st);
+        if (!prof && epi == EPI_PIPE) return launch_gemm<1, false, 2, 2, true>(ma, mb, P, grid, st);
+        if (prof && epi == EPI_PIPE) return launch_gemm<1, true, 2, 2, true>(ma, mb, P, grid, st);
+    }
+    if (mc) return OFB_EUNSUPPORTED;
 #undef OFB_GEMM_CASE
     return OFB_EINVAL;
 }
@@ -790,7 +1068,7 @@ int corr_pyramid_impl(const void* f1_km, const void* f2_km, const void* f2q_km, 
                       int w, float scale, int cta_group, unsigned long long* prof, void* stream) {
     if (B == 0) return OFB_OK;   // nothing to do: empty tensors have no storage, their pointers may be null
     if (!f1_km || !f2_km || !pyr || B < 0 || C <= 0 || h <= 0 || w <= 0) return OFB_EINVAL;
-    if (cta_group < 0 || cta_group > 2) return OFB_EINVAL;
+    if (cta_group < 0 || cta_group > 3) return OFB_EINVAL;
     if (pyr->levels < 1 || pyr->levels > OFB_MAX_LEVELS) return OFB_EINVAL;
     if (pyr->dtype != OFB_DTYPE_BF16) return OFB_EUNSUPPORTED;          // fp32 pyramids: ofb_corr_pyramid_simt_f32
     if (C % BLOCK_K != 0 || C > MAX_KB * BLOCK_K) return OFB_EUNSUPPORTED;
@@ -811,10 +1089,14 @@ int corr_pyramid_impl(const void* f1_km, const void* f2_km, const void* f2q_km, 
             return OFB_EINVAL;
     }
     if (pyr->layout < OFB_LAYOUT_ROWS || pyr->layout > OFB_LAYOUT_QMINOR8X4) return OFB_EINVAL;
-    // auto: one CTA per tile -- measured faster than the CTA pair on every BASELINE shape once the
-    // kernel became HBM-write-bound (profiles/r01_k2_findings.md); the pair halves operand traffic but
-    // couples two epilogues through one accumulator barrier
-    const int cg = cta_group == 0 ? 1 : cta_group;
+    // auto (round-2 measurements, profiles/r02_k2_*.jsonl): the builder runs into the 1 kW power cap, so what pays is
+    // energy per tile.  Clusters of two independent cta_group::1 CTAs with the fmap2 ring multicast into both (mode 3)
+    // halve the L2 -> SM operand traffic and are 3-5 % faster than one CTA per tile at every BASELINE shape in sustained
+    // runs; the CTA pair (cta_group::2) is slower (its MMAs run below the single-CTA rate and the pair's epilogues are
+    // coupled through one accumulator barrier).  Mode 3 is built for the product layout only.
+    int cg = cta_group;
+    if (cg == 0) cg = (pyr->layout == OFB_LAYOUT_QMINOR8X4 && h * w > BLOCK_M) ? 3 : 1;
+    if (cg == 3 && pyr->layout != OFB_LAYOUT_QMINOR8X4) return OFB_EUNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
     const int rc = run_gemm(f1_km, f2_km, pyr, 0, pyr->levels > 1 ? 1 : -1, B, C, h * w, h, w, scale, cg, prof, 0, st);
     if (rc != OFB_OK || pyr->levels <= 2) return rc;
