@@ -348,30 +348,46 @@ def run_ours(args):
     # ---- end-to-end arm: pinned host inputs, copies inside the timed region
     # the producer writes each pair's inputs into a pinned pair-major arena (ofb200.runner.PairArena): the runner
     # then moves one micro-batch -- all eight input tensors -- with a single host->device DMA
-    host = PairArena(pairs, PairArena.shapes_of(batch), pin=True).fill(batch)
-    runner = HostStagedRunner(device, min(args.e2e_micro, pairs))
-    m2 = AverageEndPointError()
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    for _ in range(2):
-        runner.run(host, m2)
-    m2.reset()
-    runner.h2d_bytes = runner.d2h_bytes = 0
-    barrier()
-    t0 = time.perf_counter()
-    e0.record()
-    for i in range(e2e_steps):
-        # every step copies its own inputs; the next step's first pair is already in flight while this step's last
-        # pair computes and its metric is read back
-        epe_e2e = runner.run(host, m2, prefetch=host if i + 1 < e2e_steps else None)
-    e1.record()
-    barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    e2e_ms = max(e0.elapsed_time(e1), wall_ms)         # host-side staging is part of the cost: take the slower clock
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    e2e_value = world * pairs * e2e_steps / (e2e_ms * 1e-3)
+    def time_e2e(dtypes):
+        host = PairArena(pairs, PairArena.shapes_of(batch), pin=True, dtypes=dtypes).fill(batch)
+        runner = HostStagedRunner(device, min(args.e2e_micro, pairs))
+        m2 = AverageEndPointError()
+        steps = max(1, min(args.steps, args.e2e_steps))
+        for _ in range(2):
+            runner.run(host, m2)
+        m2.reset()
+        runner.h2d_bytes = runner.d2h_bytes = 0
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(steps):
+            # every step copies its own inputs; the next step's first pair is already in flight while this step's last
+            # pair computes and its metric is read back
+            epe = runner.run(host, m2, prefetch=host if i + 1 < steps else None)
+        e1.record()
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        ms_ = max(e0.elapsed_time(e1), wall_ms)        # host-side staging is part of the cost: take the slower clock
+        if world > 1:
+            t = torch.tensor([ms_], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_ = float(t.item())
+        res = {"value": round(world * pairs * steps / (ms_ * 1e-3), 2), "unit": UNIT, "steps": steps,
+               "h2d_bytes_per_step": runner.h2d_bytes // steps, "d2h_bytes_per_step": runner.d2h_bytes // steps,
+               "ms_per_step": round(ms_ / steps, 3), "micro_batch": runner.micro, "epe": epe}
+        del host, runner
+        return res
+
+    # headline: the feature maps travel in bf16, the precision the reference's shipped configs produce them in
+    # (`precision: 16`, methods/raft/config/train/default.yaml:20); everything else fp32.  The correlation operands
+    # are bf16 either way (1/sqrt(256) is a power of two), so the pyramid is bit-identical to the fp32-input pass.
+    half = {"fmap1": torch.bfloat16, "fmap2": torch.bfloat16}
+    e2e = time_e2e(half)
+    e2e["input_dtypes"] = "fmap1, fmap2: bf16 (read directly by ofb_corr_prep_from); coords, flow_lo, up_mask, frame, target, valid: fp32"
+    e2e_fp32 = time_e2e(None)
+    e2e_fp32["input_dtypes"] = "all fp32 (round-1 configuration)"
+    epe_e2e = e2e.pop("epe")
+    e2e_fp32.pop("epe")
     if rank == 0:
         sampler.stop()
 
@@ -424,10 +440,8 @@ def run_ours(args):
                    "l2": "inputs larger than L2 (pyramid 2.83 GB/pair, 196 MB of inputs per pair)",
                    "parallelism": f"batch-sharded x{world}, NCCL all-reduce of (sum_epe, count) only",
                    "host_affinity": affinity},
-        "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "steps": e2e_steps,
-                "h2d_bytes_per_step": runner.h2d_bytes // e2e_steps, "d2h_bytes_per_step": runner.d2h_bytes // e2e_steps,
-                "ms_per_step": round(e2e_ms / e2e_steps, 3), "micro_batch": runner.micro,
-                "api": "ofb200.runner.HostStagedRunner.run(pinned PairArena: one DMA per pair) -> CorrBlock / warp / upsample_flow / AverageEndPointError -> libofb200 C ABI"},
+        "e2e": dict(e2e, api="ofb200.runner.HostStagedRunner.run(pinned PairArena: one DMA per pair) -> CorrBlock / warp / upsample_flow / AverageEndPointError -> libofb200 C ABI"),
+        "e2e_fp32_inputs": e2e_fp32,
         "gpu_launches": int(launches),
         "clocks": sampler.summary(t_wall0, t_wall1),
         "roofline": roofline,
@@ -437,7 +451,7 @@ def run_ours(args):
     if world == 1 and not args.no_named:
         line["named_configs"] = named_kernel_table(torch)
     if world == 1 and not args.no_cpu:
-        del batch, views, host, runner
+        del batch, views
         torch.cuda.empty_cache()
         cb = time_cpu(1, 0, 1)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "ports")}

@@ -96,9 +96,9 @@ def test_reference_assertion_behaviour():
 
 
 def test_pair_arena_layout_cpu():
-    """ofb200.runner.PairArena (host logic, no GPU): every field is a view of one (pairs, floats_per_pair) buffer at a
-    256-byte aligned offset, with the field's usual shape; a pair's fields are contiguous in memory so a micro-batch
-    is one slice of rows."""
+    """ofb200.runner.PairArena (host logic, no GPU): every field is a view of one (pairs, bytes_per_pair) buffer at a
+    256-byte aligned offset, with the field's usual shape and its own dtype; a pair's fields are contiguous in memory so
+    a micro-batch is one slice of rows."""
     import torch
 
     from ofb200.runner import FIELDS, PairArena
@@ -110,17 +110,24 @@ def test_pair_arena_layout_cpu():
              "up_mask": torch.randn(pairs, 576, h, w, generator=g), "frame": torch.rand(pairs, 3, 8 * h, 8 * w, generator=g),
              "target": torch.randn(pairs, 2, 8 * h, 8 * w, generator=g), "valid": torch.rand(pairs, 8 * h, 8 * w, generator=g)}
     arena = PairArena(pairs, PairArena.shapes_of(batch)).fill(batch)
-    assert arena.buf.shape == (pairs, arena.pair_floats) and arena.pair_floats % PairArena.ALIGN == 0
+    assert arena.buf.shape == (pairs, arena.pair_bytes) and arena.pair_bytes % PairArena.ALIGN == 0
     for k in FIELDS:
         assert arena.offsets[k] % PairArena.ALIGN == 0
         assert arena[k].shape == batch[k].shape and torch.equal(arena[k], batch[k])
-        assert arena[k].data_ptr() == arena.buf.data_ptr() + 4 * arena.offsets[k]          # a view, not a copy
+        assert arena[k].data_ptr() == arena.buf.data_ptr() + arena.offsets[k]              # a view, not a copy
     # a micro-batch is a row range: its views see the same values
     for k in FIELDS:
         sub = arena.view(k, 1, 3)
         want = batch[k][:, 1:3] if k == "coords" else batch[k][1:3]
         assert torch.equal(sub, want)
     assert arena.payload_bytes_per_pair == 4 * sum(batch[k].numel() for k in FIELDS) // pairs
+    # half-precision feature maps travel as they are: same views, half the bytes for those fields
+    half = PairArena(pairs, PairArena.shapes_of(batch), dtypes={"fmap1": torch.bfloat16, "fmap2": torch.float16}).fill(batch)
+    assert half["fmap1"].dtype == torch.bfloat16 and half["fmap2"].dtype == torch.float16 and half["up_mask"].dtype == torch.float32
+    assert torch.equal(half["fmap1"], batch["fmap1"].bfloat16()) and torch.equal(half["fmap2"], batch["fmap2"].half())
+    assert torch.equal(half["coords"], batch["coords"]) and torch.equal(half.view("frame", 1, 2), batch["frame"][1:2])
+    assert half.payload_bytes_per_pair == arena.payload_bytes_per_pair - 2 * 2 * batch["fmap1"][0].numel()
+    assert not half.same_layout(arena) and half.same_layout(half)
 
 
 def test_input_padder_known_answers_cpu():

@@ -728,6 +728,18 @@ def test_host_staged_runner_arena_matches_dict():
             got = runner.run(arena if nxt is not other else arena, AverageEndPointError(), prefetch=nxt)
             assert abs(got - want) <= 1e-6 * abs(want), (micro, "prefetch")
         assert abs(runner.run(other, AverageEndPointError()) - want) <= 1e-6 * abs(want)   # a stale prefetch is ignored
+    # half-precision feature maps in the arena: fewer bytes over the link, same result (the EPE does not depend on them;
+    # the lookup output must match a device-resident pass on the same rounded maps)
+    half = PairArena(pairs, PairArena.shapes_of(batch), pin=True,
+                     dtypes={"fmap1": torch.bfloat16, "fmap2": torch.bfloat16}).fill(batch)
+    runner = HostStagedRunner(torch.device("cuda", 0), 1)
+    got = runner.run(half, AverageEndPointError())
+    assert abs(got - want) <= 1e-6 * abs(want)
+    assert runner.h2d_bytes < sum(batch[k].numel() * 4 for k in FIELDS)
+    ref_out = hot_path(dict(batch, fmap1=batch["fmap1"].bfloat16().float(), fmap2=batch["fmap2"].bfloat16().float()),
+                       AverageEndPointError())["corr"]
+    got_out = hot_path({k: half[k].cuda() for k in FIELDS}, AverageEndPointError())["corr"]
+    assert torch.equal(ref_out, got_out)
 
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])

@@ -99,31 +99,38 @@ LAUNCHES_PER_PASS = lambda iters: 5 + iters + 1 + 1 + 1  # noqa: E731  (prep x3,
 
 
 class PairArena:
-    """Pair-major staging memory: one fp32 buffer of shape (pairs, floats_per_pair) in which every field of a pair
-    sits at a fixed, 256-byte aligned offset; `arena[name]` is a strided VIEW with the field's usual shape
+    """Pair-major staging memory: one byte buffer of shape (pairs, bytes_per_pair) in which every field of a pair
+    sits at a fixed, 256-byte aligned offset; `arena[name]` is a strided VIEW with the field's usual shape and dtype
     ((pairs, ...), and (iters, pairs, 2, h, w) for `coords`).  A producer (data loader, upstream network) fills the
     views of a pinned host arena; HostStagedRunner then moves a whole micro-batch -- all eight fields -- with ONE
     host->device DMA into a device arena of the same layout instead of one copy per field and per iteration
-    (19 copies per pair at the bench shape, each paying its launch + DMA start-up)."""
+    (19 copies per pair at the bench shape, each paying its launch + DMA start-up).
 
-    ALIGN = 64   # floats
+    `dtypes` (default fp32 everywhere) lets a field travel in the precision its producer has: the reference's shipped
+    configs run `precision: 16` (methods/raft/config/train/default.yaml:20), so the feature maps leave the encoder in
+    half precision; CorrBlock reads bf16 / fp16 maps directly (ofb_corr_prep_from), which halves their share of the
+    host->device bytes (67 -> 33 MB per 1080p pair)."""
 
-    def __init__(self, pairs: int, shapes: Dict[str, tuple], device=None, pin: bool = False) -> None:
+    ALIGN = 256   # bytes
+
+    def __init__(self, pairs: int, shapes: Dict[str, tuple], device=None, pin: bool = False,
+                 dtypes: Optional[Dict[str, torch.dtype]] = None) -> None:
         """shapes[name] = the field's per-pair shape; `coords` as (iters, 2, h, w)."""
         self.pairs, self.shapes, self.offsets = pairs, dict(shapes), {}
+        self.dtypes = {k: (dtypes or {}).get(k, torch.float32) for k in FIELDS}
         off = 0
+        payload = 0
         for k in FIELDS:
             self.offsets[k] = off
-            n = 1
-            for d in shapes[k]:
-                n *= int(d)
-            off += (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
-        self.pair_floats = off
-        self.payload_bytes_per_pair = 4 * sum(int(torch.Size(shapes[k]).numel()) for k in FIELDS)
+            nbytes = int(torch.Size(shapes[k]).numel()) * self.dtypes[k].itemsize
+            payload += nbytes
+            off += (nbytes + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.pair_bytes = off
+        self.payload_bytes_per_pair = payload
         if device is None:
-            self.buf = torch.empty((pairs, off), dtype=torch.float32, pin_memory=pin)
+            self.buf = torch.empty((pairs, off), dtype=torch.uint8, pin_memory=pin)
         else:
-            self.buf = torch.empty((pairs, off), dtype=torch.float32, device=device)
+            self.buf = torch.empty((pairs, off), dtype=torch.uint8, device=device)
 
     @staticmethod
     def shapes_of(batch: Dict[str, Tensor]) -> Dict[str, tuple]:
@@ -134,12 +141,15 @@ class PairArena:
             out[k] = (sh[0],) + sh[2:] if k == "coords" else sh[1:]
         return out
 
+    def same_layout(self, other: "PairArena") -> bool:
+        return self.shapes == other.shapes and self.dtypes == other.dtypes
+
     def view(self, name: str, lo: int = 0, hi: Optional[int] = None) -> Tensor:
         hi = self.pairs if hi is None else hi
         sh = self.shapes[name]
-        n = int(torch.Size(sh).numel())
-        flat = self.buf[lo:hi, self.offsets[name]:self.offsets[name] + n]
-        v = flat.view(hi - lo, *sh)
+        nbytes = int(torch.Size(sh).numel()) * self.dtypes[name].itemsize
+        flat = self.buf[lo:hi, self.offsets[name]:self.offsets[name] + nbytes]
+        v = flat.view(self.dtypes[name]).view(hi - lo, *sh)
         return v.transpose(0, 1) if name == "coords" else v
 
     def __getitem__(self, name: str) -> Tensor:
@@ -191,12 +201,12 @@ class HostStagedRunner:
 
     def _stage_arena(self, slot: int, host: PairArena, lo: int, hi: int) -> None:
         cur = self.slots[slot]
-        if not isinstance(cur, PairArena) or cur.pairs != hi - lo or cur.shapes != host.shapes:
-            self.slots[slot] = PairArena(hi - lo, host.shapes, device=self.device)
+        if not isinstance(cur, PairArena) or cur.pairs != hi - lo or not cur.same_layout(host):
+            self.slots[slot] = PairArena(hi - lo, host.shapes, device=self.device, dtypes=host.dtypes)
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self.freed[slot])       # previous user of this slot has finished
             self.slots[slot].buf.copy_(host.buf[lo:hi], non_blocking=True)   # whole rows: one contiguous DMA
-            self.h2d_bytes += (hi - lo) * host.pair_floats * 4      # what the DMA moves (payload + <= 2 KB of alignment padding per pair)
+            self.h2d_bytes += (hi - lo) * host.pair_bytes           # what the DMA moves (payload + <= 2 KB of alignment padding per pair)
             self.ready[slot].record(self.copy_stream)
 
     def _run_arena(self, host: PairArena, metric: AverageEndPointError, prefetch: Optional[PairArena]) -> float:
