@@ -289,17 +289,25 @@ def run_ours(args):
     ofb200.load()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    device = torch.device("cuda", local)
-    affinity = bind_to_gpu_numa_node(torch, local) if world > 1 else "default"
+    placement = {"chosen": "default"}
+    dev_index = local
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+        # gloo for the CPU-side coordination of the placement probe, NCCL for everything on the device
+        dist.init_process_group("cpu:gloo,cuda:nccl")
+        if not args.no_placement:
+            from ofb200.runner import choose_device_set
+
+            dev_index, placement = choose_device_set(rank, world, local)
+    torch.cuda.set_device(dev_index)
+    device = torch.device("cuda", dev_index)
+    affinity = bind_to_gpu_numa_node(torch, dev_index) if world > 1 else "default"
     if world != args.gpus and rank == 0:
         sys.stderr.write(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}\n")
+    sync_flag = torch.zeros(1, device=device)
 
     def barrier():
         if world > 1:
-            dist.barrier()
+            dist.all_reduce(sync_flag)                 # a device collective (NCCL): every rank's stream has reached this point
         torch.cuda.synchronize()
 
     pairs, micro = args.pairs, min(args.micro, args.pairs)
@@ -320,7 +328,7 @@ def run_ours(args):
     for _ in range(args.warmup):
         step()
     metric.reset()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(dev_index)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
@@ -439,7 +447,7 @@ def run_ours(args):
                    "micro_batch": micro, "iters": ITERS, "radius": RADIUS, "levels": LEVELS,
                    "l2": "inputs larger than L2 (pyramid 2.83 GB/pair, 196 MB of inputs per pair)",
                    "parallelism": f"batch-sharded x{world}, NCCL all-reduce of (sum_epe, count) only",
-                   "host_affinity": affinity},
+                   "host_affinity": affinity, "device_placement": placement},
         "e2e": dict(e2e, api="ofb200.runner.HostStagedRunner.run(pinned PairArena: one DMA per pair) -> CorrBlock / warp / upsample_flow / AverageEndPointError -> libofb200 C ABI"),
         "e2e_fp32_inputs": e2e_fp32,
         "gpu_launches": int(launches),
@@ -473,6 +481,7 @@ def main():
     ap.add_argument("--cta-group", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-named", action="store_true", help="skip the single-kernel named configs")
+    ap.add_argument("--no-placement", action="store_true", help="ranks use cuda:LOCAL_RANK without probing the host links")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3                                   # timing rule: at least 3 warm-up steps

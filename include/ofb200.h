@@ -201,8 +201,8 @@ int ofb_pyramid_layout(int h, int w, int levels, int mode, ofb_pyramid* pyr_host
  * levels 1.. = 2x2 average pooling over the target (q) image, complete blocks only.
  *
  * Step 1, ofb_corr_prep_bf16: fmap (B,C,h,w) fp32 NCHW -> K-major bf16 operand
- *         (B, (h/pool)*(w/pool), C), multiplied by `scale` and, for pool = 4, averaged over complete
- *         4x4 blocks (cast + transpose in one pass; replaces the .view/.transpose of corr.py:82-85).
+ *         (B, (h/pool)*(w/pool), C), multiplied by `scale` and, for pool = 2, 4, 8, averaged over complete
+ *         pool x pool blocks (cast + transpose in one pass; replaces the .view/.transpose of corr.py:82-85).
  *         The caller preps fmap1 with scale = 1/sqrt(C) (corr.py:87) and fmap2 twice: pool = 1 and,
  *         for pyramids with more than 2 levels, pool = 4.
  * Step 2, ofb_corr_pyramid_bf16: tcgen05/TMEM GEMM tiles fed by TMA, bf16 x bf16 -> fp32
@@ -227,6 +227,18 @@ int ofb_corr_prep_from(const void* fmap_nchw, int in_dtype, void* out_km_bf16, i
                        float scale, void* stream);
 int ofb_corr_pyramid_bf16(const void* f1_km, const void* f2_km, const void* f2q_km, const ofb_pyramid* pyr_host,
                           int B, int C, int h, int w, float scale, int cta_group, void* stream);
+/* On-demand correlation lookup: CorrBlock.__call__ (corr.py:56-77) WITHOUT the materialised
+ * volume of corr.py:45-54.  avg_pool2d is linear, so level l of the pyramid is f1^T . avgpool_l(f2) / sqrt(C); the kernel
+ * evaluates those dot products only at the positions each query's window touches and samples them with the same bit-exact
+ * coordinate sequence as ofb_corr_lookup.
+ *   f1_km            (B, h*w, C) bf16 K-major, already multiplied by 1/sqrt(C)      (ofb_corr_prep_from, pool 1)
+ *   f2_km_levels[l]  (B, (h>>l)*(w>>l), C) bf16 K-major, fmap2 averaged over complete 2^l x 2^l blocks (pool 1, 2, 4, 8)
+ *   coords (B,2,h,w) fp32 -> out (B, levels*(2r+1)^2, h, w) fp32.  C in {64, 128, 256}.
+ * Memory: the operand maps (22 MB per 1088x1920 pair) instead of the 2.83 GB pyramid; it is slower than build + lookup
+ *  -- a capacity feature. */
+int ofb_corr_lookup_ondemand(const void* f1_km, const void* const* f2_km_levels_host, const float* coords, float* out,
+                             int B, int C, int h, int w, int levels, int radius, void* stream);
+
 /* Diagnostics build of the same kernel: additionally fills prof_dev[2][148][16] (device, uint64; one
  * slot per GEMM run) with per-CTA cycle counters -- [0] TMA warp waiting for a free fmap2 stage,
  * [1] for a free fmap1 block, [2] MMA warp waiting for fmap1, [3] for a drained TMEM accumulator,

@@ -633,6 +633,50 @@ def test_corr_block_half_precision_feature_maps(dt):
             assert rel <= 4e-3 and mx <= 4e-2
 
 
+@pytest.mark.parametrize("shape", [(2, 256, 47, 156), (1, 128, 24, 40), (1, 64, 19, 37), (1, 256, 136, 240)])
+def test_corr_block_on_demand_matches_materialised(shape):
+    """lookups without a materialised volume.  Same floor indices by construction (same coordinate
+    code path as the oracle-checked kernels); values against (1) the fp32 CUDA-core pyramid + lookup -- the reference's
+    arithmetic -- within the bf16-operand tolerance (rel-Frobenius <= 4e-3: here only the OPERANDS are bf16, the
+    correlation values themselves stay fp32), (2) the CPU oracle on the small shapes; zeros outside the image, finite
+    output for non-finite coordinates."""
+    from model.corr import CorrBlock
+    from model.utils import coords_grid
+
+    b, c, h, w = shape
+    gen = torch.Generator(device="cuda").manual_seed(71)
+    f1 = torch.randn(shape, device="cuda", generator=gen)
+    f2 = torch.randn(shape, device="cuda", generator=gen)
+    od = CorrBlock(f1, f2, on_demand=True)
+    assert od.builder == "on_demand"
+    base = coords_grid(b, h, w).cuda()
+    kinds = {"int": base, "noise": base + 4 * torch.randn((b, 2, h, w), device="cuda", generator=gen),
+             "far": base + 60 * torch.randn((b, 2, h, w), device="cuda", generator=gen)}
+    nonf = base.clone()
+    nonf[:, 0, ::3, ::5] = 1e9
+    nonf[:, 1, 1::4, 2::7] = float("nan")
+    kinds["nonfinite"] = nonf
+    ref_blk = CorrBlock(f1, f2, pyramid_dtype=torch.float32, builder="simt") if h * w <= 8000 else CorrBlock(f1, f2)
+    for kind, coords in kinds.items():
+        got = od(coords)
+        assert got.shape == (b, 324, h, w) and torch.isfinite(got).all(), kind
+        want = ref_blk(coords)
+        rel = float((got - want).norm() / want.norm().clamp_min(1e-6))
+        assert rel <= (4e-3 if h * w <= 8000 else 6e-3), (kind, rel)
+    if h * w <= 1000:
+        f1r, f2r = oracle.round_bf16(N(f1) / np.float32(np.sqrt(c))) * np.float32(np.sqrt(c)), N(f2)
+        pyr = oracle.corr_pyramid(N(f1), N(f2), 4)
+        ref = oracle.corr_lookup(pyr, N(kinds["noise"]), 4)
+        got = N(od(kinds["noise"]))
+        assert np.linalg.norm(got - ref) / np.linalg.norm(ref) <= 4e-3
+    with pytest.raises(NotImplementedError):
+        od.corr_pyramid
+    with pytest.raises(NotImplementedError):
+        od(base, return_index=True)
+    with pytest.raises(NotImplementedError):
+        CorrBlock(f1.requires_grad_(), f2, on_demand=True)
+
+
 def test_empty_batches():
     """Zero-size inputs: every op returns an empty tensor of the right shape (as the ATen ops behind the reference
     do) instead of tripping over the null data pointer of an empty tensor; metrics stay untouched."""

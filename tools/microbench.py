@@ -2,7 +2,7 @@
 3 warm-ups, inputs rotated / larger than L2).  One record per kernel with the algorithmic
 bytes / flops of SURVEY.md section 8d and the achieved fraction of the measured peaks.
 
-    python tools/microbench.py [warp] [corr] [lookup] [upsample] [corr_big]
+    python tools/microbench.py [warp] [corr] [lookup] [upsample] [corr_big] [ondemand]
 
 bench.py imports bench_warp_c2 / bench_corr_c3 / bench_lookup_c4 for its `named_configs` table."""
 import ctypes
@@ -167,6 +167,26 @@ def bench_lookup(name, blk, gen, b, h, w, iters=12):
     ms = timeit(look, reps=5) / iters
     return record(f"{name} K3 lookup r=4 x{iters} ({'bf16' if esz == 2 else 'fp32'} pyramid), per iteration", ms,
                   nbytes=b * n * (4 * 100 * esz + 8 + 324 * 4), iters_ms=round(iters * ms, 3))
+
+
+def bench_ondemand(name, b, c, h, w, iters=12):
+    """On-demand correlation lookup (no materialised volume): time per iteration, and the memory it needs."""
+    gen, f1, f2 = _corr_setup(b, c, h, w, seed=3)
+    torch.cuda.reset_peak_memory_stats()
+    m0 = torch.cuda.memory_allocated()
+    blk = CorrBlock(f1, f2, on_demand=True)
+    mem = torch.cuda.memory_allocated() - m0
+    coords = coords_grid(b, h, w).cuda()[None] + 4 * torch.randn((iters, b, 2, h, w), device="cuda", generator=gen)
+    out = torch.empty((b, 324, h, w), device="cuda")
+
+    def look():
+        for it in range(iters):
+            blk(coords[it], out=out)
+    ms = timeit(look, reps=3, warm=1) / iters
+    n = h * w
+    macs = 4 * 121 * c                                    # <= 11 x 11 positions per level
+    return record(f"{name} on-demand corr lookup r=4 x{iters}, per iteration", ms, flops=2.0 * b * n * macs,
+                  operand_bytes_per_pair=round(mem / b), pyramid_bytes_per_pair_bf16=2 * n * sum((h >> l) * (w >> l) for l in range(4)))
 
 
 def bench_lookup_c4():
@@ -359,6 +379,8 @@ def main():
             emit([bench_lookup(name, blk, gen, shp[0], shp[2], shp[3])])
             del blk
             torch.cuda.empty_cache()
+    if "ondemand" in which:
+        emit([bench_ondemand("C4 B16 47x156", 16, 256, 47, 156), bench_ondemand("C5 B8 136x240", 8, 256, 136, 240)])
 
 
 if __name__ == "__main__":

@@ -177,7 +177,9 @@ static int launch_prep(const void* fmap, __nv_bfloat16* out, int B, int C, int h
     const size_t smem = (size_t)(C < TCMAX ? C : TCMAX) * (TP + 1) * sizeof(float);      // <= 33 KiB
     const TIn* in = reinterpret_cast<const TIn*>(fmap);
     if (pool == 1) prep_kernel<1, TIn><<<grid, 256, smem, st>>>(in, out, C, h, w, scale);
-    else prep_kernel<4, TIn><<<grid, 256, smem, st>>>(in, out, C, h, w, scale);
+    else if (pool == 2) prep_kernel<2, TIn><<<grid, 256, smem, st>>>(in, out, C, h, w, scale);
+    else if (pool == 4) prep_kernel<4, TIn><<<grid, 256, smem, st>>>(in, out, C, h, w, scale);
+    else prep_kernel<8, TIn><<<grid, 256, smem, st>>>(in, out, C, h, w, scale);
     OFB_LAUNCH_CHECK();
     return OFB_OK;
 }
@@ -186,7 +188,7 @@ OFB_API int ofb_corr_prep_from(const void* fmap_nchw, int in_dtype, void* out_km
                                float scale, void* stream) {
     if (B == 0) return OFB_OK;   // nothing to do: empty tensors have no storage, their pointers may be null
     if (!fmap_nchw || !out_km_bf16 || B < 0 || C <= 0 || h <= 0 || w <= 0) return OFB_EINVAL;
-    if (pool != 1 && pool != 4) return OFB_EINVAL;
+    if (pool != 1 && pool != 2 && pool != 4 && pool != 8) return OFB_EINVAL;
     if (in_dtype != OFB_DTYPE_F32 && in_dtype != OFB_DTYPE_BF16 && in_dtype != OFB_DTYPE_F16) return OFB_EINVAL;
     if (C & 1) return OFB_EUNSUPPORTED;
     if (reinterpret_cast<uintptr_t>(out_km_bf16) & 3) return OFB_EALIGN;

@@ -73,6 +73,7 @@ SIGNATURES = {
     "ofb_cast_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, ctypes.c_longlong, ctypes.c_longlong, _vp]),
     "ofb_corr_lookup_backward_f32": (_i, [ctypes.POINTER(Pyramid), _vp, _vp, _i, _i, _i, _i, _vp]),
     "ofb_corr_lookup": (_i, [ctypes.POINTER(Pyramid), _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "ofb_corr_lookup_ondemand": (_i, [_vp, ctypes.POINTER(_vp), _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "ofb_bilinear_sampler_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
 }
 

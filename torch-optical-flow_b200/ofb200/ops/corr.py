@@ -221,7 +221,15 @@ class CorrBlock:
         pyramid_dtype: Optional[torch.dtype] = None,
         builder: str = "auto",
         cta_group: int = 0,
+        on_demand: Optional[bool] = None,
     ) -> None:
+        """fmap1, fmap2 (B, C, h, w) in fp32 / bf16 / fp16 (reference corr.py:38-54).
+
+        Extensions (keyword-only, defaults keep the reference's behaviour): `pyramid_dtype` (bf16 default, fp32 selects
+        the CUDA-core builder), `builder`, `cta_group` (K2 launch mode), and `on_demand=True` (or
+        OFB200_CORR_ON_DEMAND=1): nothing is materialised -- every lookup evaluates the correlation values of its own
+        windows from the operand maps (ofb_corr_lookup_ondemand; 22 MB instead of 2.83 GB per 1080p pair, slower per
+        lookup; forward-only)."""
         self.num_levels = num_levels
         self.radius = radius
         if fmap1.shape != fmap2.shape or fmap1.dim() != 4:
@@ -251,6 +259,30 @@ class CorrBlock:
         self._shape = (b, c, h, w)
         self._dev = fmap1.device
         lib = ofb200.load()
+        if on_demand is None:
+            on_demand = os.environ.get("OFB200_CORR_ON_DEMAND", "0") not in ("", "0")
+        self._on_demand = None
+        if on_demand:
+            if diff_maps is not None:
+                raise NotImplementedError("CorrBlock(on_demand=True) is forward-only: the feature maps must not require grad")
+            if c not in (64, 128, 256) or radius > 4:
+                raise NotImplementedError("CorrBlock(on_demand=True) needs C in {64, 128, 256} and radius <= 4")
+            self.builder = "on_demand"
+            self._buffers, self._views, self._pyr = [], None, None
+            scale = 1.0 / math.sqrt(float(c))
+            st = ofb200.stream_ptr()
+            with torch.cuda.device(self._dev):
+                a_km = torch.empty((b, h * w, c), dtype=torch.bfloat16, device=self._dev)
+                ofb200.check(lib.ofb_corr_prep_from(ofb200.ptr(fmap1), _IN_DTYPES[fmap1.dtype], ofb200.ptr(a_km), b, c, h, w, 1,
+                                                    scale, st), "ofb_corr_prep_from")
+                levels = []
+                for lvl in range(num_levels):
+                    f2l = torch.empty((b, (h >> lvl) * (w >> lvl), c), dtype=torch.bfloat16, device=self._dev)
+                    ofb200.check(lib.ofb_corr_prep_from(ofb200.ptr(fmap2), _IN_DTYPES[fmap2.dtype], ofb200.ptr(f2l), b, c, h, w,
+                                                        1 << lvl, 1.0, st), "ofb_corr_prep_from")
+                    levels.append(f2l)
+            self._on_demand = (a_km, levels)
+            return
         tc_ok = pyramid_dtype == torch.bfloat16 and c % 64 == 0 and c <= 256
         if builder == "auto":
             builder = "tcgen05" if tc_ok else "simt"
@@ -310,6 +342,8 @@ class CorrBlock:
         Row layout: strided views of the padded buffers.  8x4-blocked layout (tcgen05 builder): the
         blocks are unfolded into a copy on first access -- the lookup never needs this, only callers
         that inspect the volume do."""
+        if self._on_demand is not None:
+            raise NotImplementedError("CorrBlock(on_demand=True) does not materialise the correlation pyramid")
         if self._views is None:
             b, _, h, w = self._shape
             n = h * w
@@ -374,6 +408,15 @@ class CorrBlock:
         with torch.cuda.device(self._dev):
             if out is None:
                 out = torch.empty((b, self.num_levels * d * d, h, w), dtype=torch.float32, device=self._dev)
+            if self._on_demand is not None:
+                if idx is not None or valid is not None:
+                    raise NotImplementedError("CorrBlock(on_demand=True): return_index is not available")
+                a_km, levels = self._on_demand
+                ptrs = (ctypes.c_void_p * ofb200.MAX_LEVELS)(*[t.data_ptr() for t in levels])
+                rc = ofb200.load().ofb_corr_lookup_ondemand(ofb200.ptr(a_km), ptrs, ofb200.ptr(coords_d), ofb200.ptr(out),
+                                                            b, c, h, w, self.num_levels, self.radius, ofb200.stream_ptr())
+                ofb200.check(rc, "ofb_corr_lookup_ondemand")
+                return out
             rc = ofb200.load().ofb_corr_lookup(
                 ctypes.byref(self._pyr), ofb200.ptr(coords_d), ofb200.ptr(out), ofb200.ptr(idx), ofb200.ptr(valid),
                 b, h, w, self.radius, ofb200.stream_ptr(),

@@ -274,6 +274,53 @@ class HostStagedRunner:
         return float(state[0] / state[1])
 
 
+def choose_device_set(rank: int, world: int, local_rank: int, probe_mb: int = 64, reps: int = 6, min_gain: float = 1.10):
+    """Topology-aware rank -> GPU placement for host-staged runs (one process per GPU, `torch.distributed` initialised
+    with a CPU-capable backend such as "cpu:gloo,cuda:nccl").
+
+    On an 8-GPU B200 host the GPUs do not all reach pinned host memory at the same rate: measured on this pool
+    (tools/h2d_probe.py, profiles/r02_scale_probe.jsonl) four ranks on GPUs 0-3 share ~115 GB/s while GPUs 4-7 take
+    55 GB/s EACH (220 GB/s) -- and nothing inside the guest (one NUMA node, no PCIe topology) says which half is
+    which.  So when more GPUs are visible than ranks, the two candidate sets {0..N-1} and {V-N..V-1} are probed:
+    every rank copies `probe_mb` from pinned memory to its GPU of the set at the same time, the slowest rank's time
+    is agreed on through the CPU backend, and the faster set is taken if it is at least `min_gain` times better.
+    Returns (device index for this rank, a dict describing the decision)."""
+    import torch.distributed as dist
+
+    visible = torch.cuda.device_count()
+    info = {"visible": visible, "sets": {}, "chosen": "default"}
+    if world < 2 or visible < 2 * world or not dist.is_initialized():
+        return local_rank, info
+    sets = {"low": list(range(world)), "high": list(range(visible - world, visible))}
+    nbytes = probe_mb << 20
+    host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    rates = {}
+    for name, devs in sets.items():
+        dev = torch.device("cuda", devs[local_rank])
+        with torch.cuda.device(dev):
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            st = torch.cuda.Stream(device=dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(st):
+                buf.copy_(host, non_blocking=True)                      # warm-up: context, link power state
+            st.synchronize()
+            dist.all_reduce(torch.zeros(1))                             # CPU tensor -> CPU backend: all ranks start together
+            with torch.cuda.stream(st):
+                e0.record(st)
+                for _ in range(reps):
+                    buf.copy_(host, non_blocking=True)
+                e1.record(st)
+            st.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)                    # CPU tensor -> CPU backend
+            rates[name] = world * nbytes * reps / (float(t.item()) * 1e-3) / 1e9
+            del buf
+        info["sets"][name] = {"devices": devs, "aggregate_h2d_gbs": round(rates[name], 1)}
+    pick = "high" if rates["high"] >= min_gain * rates["low"] else "low"
+    info["chosen"] = pick
+    return sets[pick][local_rank], info
+
+
 def shard_range(total: int, rank: int, world: int):
     """Contiguous batch slice [lo, hi) of `total` pairs owned by `rank` (pairs never cross GPUs)."""
     if not (0 <= rank < world):
