@@ -246,7 +246,15 @@ def named_kernel_table(torch):
     import microbench
 
     recs = []
-    for fn in (microbench.bench_warp_c2, microbench.bench_corr_c3, microbench.bench_lookup_c4):
+    # C2 / C3 / C4 forward kernels, then the training-path numbers (a driver line with clocks has to
+    # carry them): the long-K backward GEMM alone at the C4 and C5 level-0 shapes, and one CorrBlock train step at KITTI size
+    def backward_gemm():
+        return microbench.bench_gemm_nt(shapes=((16, 7332, 256, 7332), (8, 32640, 256, 32640)))
+
+    def corr_train_step():
+        return microbench.bench_corr_train_c4(b=4)
+
+    for fn in (microbench.bench_warp_c2, microbench.bench_corr_c3, microbench.bench_lookup_c4, backward_gemm, corr_train_step):
         try:
             recs.extend(fn())
         except Exception as e:  # a side table must never take the headline down

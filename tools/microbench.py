@@ -169,14 +169,15 @@ def bench_lookup(name, blk, gen, b, h, w, iters=12):
                   nbytes=b * n * (4 * 100 * esz + 8 + 324 * 4), iters_ms=round(iters * ms, 3))
 
 
-def bench_ondemand(name, b, c, h, w, iters=12):
-    """On-demand correlation lookup (no materialised volume): time per iteration, and the memory it needs."""
+def bench_ondemand(name, b, c, h, w, iters=12, sigma=4.0):
+    """On-demand correlation lookup (no materialised volume): time per iteration, and the memory it needs.
+    sigma: px of white noise on the lookup coordinates (4 = the bench's; 0.25 = a smooth flow field)."""
     gen, f1, f2 = _corr_setup(b, c, h, w, seed=3)
     torch.cuda.reset_peak_memory_stats()
     m0 = torch.cuda.memory_allocated()
     blk = CorrBlock(f1, f2, on_demand=True)
     mem = torch.cuda.memory_allocated() - m0
-    coords = coords_grid(b, h, w).cuda()[None] + 4 * torch.randn((iters, b, 2, h, w), device="cuda", generator=gen)
+    coords = coords_grid(b, h, w).cuda()[None] + sigma * torch.randn((iters, b, 2, h, w), device="cuda", generator=gen)
     out = torch.empty((b, 324, h, w), device="cuda")
 
     def look():
@@ -185,7 +186,7 @@ def bench_ondemand(name, b, c, h, w, iters=12):
     ms = timeit(look, reps=3, warm=1) / iters
     n = h * w
     macs = 4 * 121 * c                                    # <= 11 x 11 positions per level
-    return record(f"{name} on-demand corr lookup r=4 x{iters}, per iteration", ms, flops=2.0 * b * n * macs,
+    return record(f"{name} on-demand corr lookup r=4 x{iters}, coords noise {sigma} px, per iteration", ms, flops=2.0 * b * n * macs,
                   operand_bytes_per_pair=round(mem / b), pyramid_bytes_per_pair_bf16=2 * n * sum((h >> l) * (w >> l) for l in range(4)))
 
 
@@ -380,7 +381,8 @@ def main():
             del blk
             torch.cuda.empty_cache()
     if "ondemand" in which:
-        emit([bench_ondemand("C4 B16 47x156", 16, 256, 47, 156), bench_ondemand("C5 B8 136x240", 8, 256, 136, 240)])
+        emit([bench_ondemand("C4 B16 47x156", 16, 256, 47, 156), bench_ondemand("C5 B8 136x240", 8, 256, 136, 240),
+              bench_ondemand("C5 B8 136x240", 8, 256, 136, 240, sigma=0.25)])
 
 
 if __name__ == "__main__":

@@ -14,8 +14,10 @@
 // them left to right side by side, so the windows of the queries in flight overlap (10 of 11 columns with the previous
 // query of the same warp, 10 of 11 rows with the neighbouring warp) and most fmap2 rows (512 B each at C = 256) come from
 // L1 instead of L2: a window is ~60 KB of operand rows, and with one level per warp and 7 CTAs per SM the first version
-// ran at the L2 -> SM limit (65 GB per iteration at the bench shape: 8.6 ms).  CTAs are persistent and capped at
-// OFB_ONDEMAND_OCC (default 2) per SM so that the working set of the resident CTAs fits the L1.  Per query a warp
+// ran at the L2 -> SM limit (65 GB per iteration at the bench shape: 8.6 ms).  CTAs are persistent, OFB_ONDEMAND_OCC
+// (default 4 = the register limit) per SM.  Measured (profiles/r02_ondemand.jsonl): with white-noise coordinates
+// (sigma = 4 px, the bench's) consecutive windows overlap by only ~1/3 and the kernel stays at the L2 -> SM limit
+// (9.4 ms per iteration for 8 pairs at 136x240); smooth coordinates reuse their rows from L1.  Per query a warp
 //   1. computes the 2*(2r+1) tap coordinates with the reference's fp32 round trip (lookup.cu),
 //   2. evaluates the <= 12 x 12 patch of dot products: lane <-> 8 consecutive channels, 32 positions per pass,
 //      one 16-byte load + 8 FMAs per position and lane, then ONE transposing butterfly (31 shuffles) turns the 32 lanes'
@@ -229,8 +231,8 @@ OFB_API int ofb_corr_lookup_ondemand(const void* f1_km, const void* const* f2_km
     static int occ = 0;
     if (!occ) {
         const char* e = getenv("OFB_ONDEMAND_OCC");                 // resident CTAs per SM (tuning override)
-        occ = e ? atoi(e) : 2;
-        if (occ < 1 || occ > 16) occ = 2;
+        occ = e ? atoi(e) : 4;
+        if (occ < 1 || occ > 16) occ = 4;
     }
     long long blocks = (long long)ofb_num_sms() * occ;
     if (blocks > P.n_items) blocks = P.n_items;
