@@ -44,7 +44,8 @@ extern "C" {
 
 #define OFB_DTYPE_F32 0
 #define OFB_DTYPE_BF16 1
-#define OFB_DTYPE_F16 2 /* input feature maps of ofb_corr_prep_from only */
+#define OFB_DTYPE_F16 2 /* input feature maps of ofb_corr_prep_from, ofb_scale_flow */
+#define OFB_DTYPE_F64 3 /* ofb_scale_flow only */
 
 #define OFB_MAX_LEVELS 4
 
@@ -91,6 +92,9 @@ int ofb_warp_grid_f32(const float* flow_bhw2, float* grid_bhw2, int B, int H, in
  * out[b,1] = in[b,1]*fy over (B,2,H,W) fp32.
  * ------------------------------------------------------------------------------------- */
 int ofb_scale_flow_f32(const float* flow, float* out, int B, int64_t HW, float fx, float fy, void* stream);
+/* The same multiply in the flow's own dtype (the reference's scale is dtype-preserving: the factor is filled into a tensor
+ * of the flow's dtype, operator.py:79-80): dtype OFB_DTYPE_F32 / F64 / F16 / BF16. */
+int ofb_scale_flow(const void* flow, void* out, int dtype, int B, int64_t HW, double fx, double fy, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * K4a  bilinear resize with per-channel magnitude rescale.

@@ -223,6 +223,41 @@ def test_scale_normalize_backward():
     assert torch.allclose(flow.grad, wgt * torch.tensor([3.0 * 6.5, -0.5 * 4.0], device="cuda").view(1, 2, 1, 1), rtol=1e-6, atol=0)
 
 
+def test_scale_is_dtype_preserving_and_epe_takes_any_dim():
+    """The reference's `scale` keeps the flow's dtype (operator.py:79-82: factor filled into a tensor of that dtype, one
+    multiply) and `end_point_error` / `AverageEndPointError` take any `dim` (epe.py:41-61)."""
+    from optical_flow import denormalize, normalize, scale
+    from optical_flow.metrics import AverageEndPointError, end_point_error
+
+    gen = torch.Generator(device="cuda").manual_seed(81)
+    for dt in (torch.float64, torch.float16, torch.bfloat16, torch.float32):
+        flow = (5 * torch.randn((2, 2, 9, 14), device="cuda", generator=gen)).to(dt)
+        for fac in ((3.0, -0.5), (2.0 / 13, 2.0 / 8), (1.0 / 3.0, 7.1)):
+            got = scale(flow, fac)
+            ref_fac = torch.stack([torch.empty_like(flow[:, 0]).fill_(fac[0]), torch.empty_like(flow[:, 1]).fill_(fac[1])], dim=1)
+            assert got.dtype == dt and torch.equal(got, flow * ref_fac), (dt, fac)
+        assert normalize(flow).dtype == dt and denormalize(flow).dtype == dt
+    with pytest.raises(NotImplementedError):
+        scale(torch.zeros((1, 2, 3, 3), dtype=torch.int32, device="cuda"), 2)
+    # EPE along other dims: (B, H, W, 2) with dim=-1 and (2, B, H, W) with dim=0 equal the (B, 2, H, W) result
+    pred = torch.randn((3, 2, 11, 17), device="cuda", generator=gen)
+    tgt = torch.randn((3, 2, 11, 17), device="cuda", generator=gen)
+    want_map = end_point_error(pred, tgt, reduce=False)
+    want = end_point_error(pred, tgt)
+    assert maxabs(N(want_map), oracle.end_point_error(N(pred), N(tgt), reduce=False)) <= 1e-6
+    for dim, perm in ((-1, (0, 2, 3, 1)), (0, (1, 0, 2, 3)), (2, (0, 2, 1, 3))):
+        p2, t2 = pred.permute(perm).contiguous(), tgt.permute(perm).contiguous()
+        got_map = end_point_error(p2, t2, dim=dim, reduce=False)
+        inv = [x for x in perm if x != 1]                         # the map keeps the remaining dims in permuted order
+        assert torch.equal(got_map, want_map.permute([sorted(inv).index(x) for x in inv]))
+        assert abs(float(end_point_error(p2, t2, dim=dim)) - float(want)) <= 1e-6 * float(want)
+        m = AverageEndPointError(dim=dim)
+        m.update(p2, t2)
+        assert abs(float(m.compute()) - float(want)) <= 1e-6 * float(want)
+    with pytest.raises(NotImplementedError):
+        end_point_error(torch.zeros(2, 3, 4, 4, device="cuda"), torch.zeros(2, 3, 4, 4, device="cuda"))
+
+
 def test_warp_channels_last_and_host_tensors():
     from optical_flow import warp
 

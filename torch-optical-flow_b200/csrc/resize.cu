@@ -99,6 +99,43 @@ __global__ void __launch_bounds__(256) scale_flow_kernel(const float* __restrict
     }
 }
 
+// scale in the flow's own dtype (the reference's scale is dtype-preserving, operator.py:59-82: the factor is filled
+// into a tensor of the flow's dtype, then one multiply).  Half types: factor rounded to the type, the exact fp32
+// product of two 8- / 11-bit significands rounded once -- what a native half multiply returns.
+template <typename T> struct ScaleT;
+template <> struct ScaleT<double> {
+    static __device__ __forceinline__ double mul(double x, double f) { return __dmul_rn(x, f); }
+    static __host__ double factor(double f) { return f; }
+};
+template <> struct ScaleT<__half> {
+    static __device__ __forceinline__ __half mul(__half x, double f) { return __float2half_rn(__fmul_rn(__half2float(x), (float)f)); }
+    static __host__ double factor(double f) { return (double)__half2float(__float2half_rn((float)f)); }
+};
+template <> struct ScaleT<__nv_bfloat16> {
+    static __device__ __forceinline__ __nv_bfloat16 mul(__nv_bfloat16 x, double f) {
+        return __float2bfloat16_rn(__fmul_rn(__bfloat162float(x), (float)f));
+    }
+    static __host__ double factor(double f) { return (double)__bfloat162float(__float2bfloat16_rn((float)f)); }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) scale_flow_any_kernel(const T* __restrict__ in, T* __restrict__ out, int B,
+                                                             int64_t HW, double fx, double fy) {
+    const int64_t total = (int64_t)B * 2 * HW;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)((t / HW) & 1);
+        out[t] = ScaleT<T>::mul(in[t], c ? fy : fx);
+    }
+}
+
+template <typename T>
+int launch_scale_any(const void* flow, void* out, int B, int64_t HW, double fx, double fy, int blocks, cudaStream_t st) {
+    scale_flow_any_kernel<T><<<blocks, 256, 0, st>>>(reinterpret_cast<const T*>(flow), reinterpret_cast<T*>(out), B, HW,
+                                                     ScaleT<T>::factor(fx), ScaleT<T>::factor(fy));
+    OFB_LAUNCH_CHECK();
+    return OFB_OK;
+}
+
 }  // namespace
 
 OFB_API int ofb_resize_bilinear_f32(const float* in, float* out, int N, int C, int H, int W, int Ho, int Wo,
@@ -161,4 +198,19 @@ OFB_API int ofb_scale_flow_f32(const float* flow, float* out, int B, int64_t HW,
     scale_flow_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(flow, out, B, HW, fx, fy);
     OFB_LAUNCH_CHECK();
     return OFB_OK;
+}
+
+OFB_API int ofb_scale_flow(const void* flow, void* out, int dtype, int B, int64_t HW, double fx, double fy, void* stream) {
+    if (dtype == OFB_DTYPE_F32)
+        return ofb_scale_flow_f32(reinterpret_cast<const float*>(flow), reinterpret_cast<float*>(out), B, HW, (float)fx, (float)fy, stream);
+    if (B == 0 || HW == 0) return OFB_OK;   // nothing to do: empty tensors have no storage, their pointers may be null
+    if (!flow || !out || B < 0 || HW < 0) return OFB_EINVAL;
+    int64_t blocks = ((int64_t)B * 2 * HW + 255) / 256;
+    const int cap = ofb_num_sms() * 32;
+    if (blocks > cap) blocks = cap;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == OFB_DTYPE_F64) return launch_scale_any<double>(flow, out, B, HW, fx, fy, (int)blocks, st);
+    if (dtype == OFB_DTYPE_F16) return launch_scale_any<__half>(flow, out, B, HW, fx, fy, (int)blocks, st);
+    if (dtype == OFB_DTYPE_BF16) return launch_scale_any<__nv_bfloat16>(flow, out, B, HW, fx, fy, (int)blocks, st);
+    return OFB_EINVAL;
 }

@@ -17,7 +17,7 @@ CSRC = os.path.join(os.path.dirname(_HERE), "csrc")
 
 MODE = {"bilinear": 0, "nearest": 1}
 PAD = {"zeros": 0, "border": 1, "reflection": 2}
-DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
+DTYPE_F32, DTYPE_BF16, DTYPE_F16, DTYPE_F64 = 0, 1, 2, 3
 LAYOUT_ROWS, LAYOUT_BLOCK8X4, LAYOUT_QMINOR8X4 = 0, 1, 2
 MAX_LEVELS = 4
 
@@ -53,6 +53,7 @@ SIGNATURES = {
     "ofb_warp_backward_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _f, _vp]),
     "ofb_warp_grid_f32": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "ofb_scale_flow_f32": (_i, [_vp, _vp, _i, _i64, _f, _f, _vp]),
+    "ofb_scale_flow": (_i, [_vp, _vp, _i, _i, _i64, ctypes.c_double, ctypes.c_double, _vp]),
     "ofb_resize_bilinear_backward_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp]),
     "ofb_resize_bilinear_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _f, _f, _vp]),
     "ofb_convex_upsample_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),

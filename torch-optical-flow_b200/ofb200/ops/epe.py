@@ -11,14 +11,28 @@ import ofb200
 
 
 def _prep(pred: Tensor, target: Tensor, dim: int):
-    if dim != 1 or pred.dim() != 4 or pred.shape[1] != 2:
-        raise NotImplementedError("end-point error kernel expects (B, 2, H, W) flows and dim=1")
+    """Device, fp32, contiguous, viewed as (L, 2, T, 1): `dim` may be any dimension holding the two flow components
+    (reference epe.py:41-61 takes any dim); the dimensions before it fold into L, those after it into T -- a free view
+    of a contiguous tensor, (B, 2, H, W) with dim=1 being the usual case."""
     if pred.shape != target.shape:
         raise RuntimeError(f"pred {tuple(pred.shape)} and target {tuple(target.shape)} differ in shape")
+    nd = pred.dim()
+    if not (-nd <= dim < nd):
+        raise IndexError(f"dim {dim} out of range for a {nd}-dimensional flow")
+    d = dim % nd
+    if pred.shape[d] != 2:
+        raise NotImplementedError(f"end-point error kernel expects 2 flow components along dim {dim}, got {pred.shape[d]}")
     for t in (pred, target):
         if t.dtype != torch.float32:
             raise NotImplementedError(f"ofb200 kernels are fp32 only, got {t.dtype}")
-    return ofb200.to_device(pred).detach().contiguous(), ofb200.to_device(target).detach().contiguous()
+    lead = 1
+    for n in pred.shape[:d]:
+        lead *= int(n)
+    trail = 1
+    for n in pred.shape[d + 1:]:
+        trail *= int(n)
+    view = (lead, 2, trail, 1)
+    return (ofb200.to_device(pred).detach().contiguous().view(view), ofb200.to_device(target).detach().contiguous().view(view))
 
 
 def _prep_valid(valid: Optional[Tensor], b: int, h: int, w: int) -> Optional[Tensor]:
@@ -107,7 +121,7 @@ class AverageEndPointError(SumCountMetric):
     """Average End-to-end Point Error (reference epe.py:8-38): streaming mean of ||pred - target||_2.
 
     Args:
-        dim: the dimension along which to compute the end-point-error (only 1 is supported)
+        dim: the dimension along which to compute the end-point-error (it must hold the 2 flow components)
     """
 
     def __init__(self, dim: int = 1) -> None:
@@ -131,6 +145,7 @@ def end_point_error(pred: Tensor, target: Tensor, dim: int = 1, reduce: bool = T
     on_host = not pred.is_cuda
     pred_d, target_d = _prep(pred, target, dim)
     b, _, h, w = pred_d.shape
+    map_shape = tuple(pred.shape[:dim % pred.dim()]) + tuple(pred.shape[dim % pred.dim() + 1:])
     if reduce:
         acc = torch.zeros(2, dtype=torch.float64, device=pred_d.device)
         _accumulate(acc, pred_d, target_d, None)
@@ -142,4 +157,5 @@ def end_point_error(pred: Tensor, target: Tensor, dim: int = 1, reduce: bool = T
                 ofb200.ptr(pred_d), ofb200.ptr(target_d), ofb200.ptr(out), b, h, w, ofb200.stream_ptr()
             )
         ofb200.check(rc, "ofb_epe_map_f32")
+        out = out.view(map_shape)
     return out.cpu() if on_host else out

@@ -136,13 +136,22 @@ def warp_grid(flow: Tensor) -> Tensor:
     return _run(run, "warp_grid", flow)
 
 
+_SCALE_DTYPES = {torch.float32: ofb200.DTYPE_F32, torch.float64: ofb200.DTYPE_F64, torch.float16: ofb200.DTYPE_F16,
+                 torch.bfloat16: ofb200.DTYPE_BF16}
+
+
 def scale(flow: Tensor, factor: Union[float, Tuple[float, float]] = 1.0) -> Tensor:
-    """Scales the optical flow by a constant in X- and Y-direction (reference operator.py:59-82)."""
+    """Scales the optical flow by a constant in X- and Y-direction (reference operator.py:59-82).
+
+    Dtype-preserving like the reference (fp32, fp64, fp16, bf16): the factor is rounded to the flow's dtype, then one
+    multiply in that dtype."""
     assert flow.size(1) == 2
     if isinstance(factor, (float, int)):
         factor = (factor, factor)
     assert len(factor) == 2
-    _check_f32(flow)
+    if flow.dtype not in _SCALE_DTYPES:
+        raise NotImplementedError(f"scale: no B200 kernel for {flow.dtype} flows (fp32, fp64, fp16, bf16)")
+    dt = _SCALE_DTYPES[flow.dtype]
     b = flow.shape[0]
     hw = flow[0, 0].numel() if b > 0 else 0
     fx, fy = float(factor[0]), float(factor[1])
@@ -150,8 +159,8 @@ def scale(flow: Tensor, factor: Union[float, Tuple[float, float]] = 1.0) -> Tens
     def run(flow_d: Tensor):
         flow_d = flow_d.contiguous()
         out = torch.empty_like(flow_d)
-        rc = ofb200.load().ofb_scale_flow_f32(ofb200.ptr(flow_d), ofb200.ptr(out), b, hw, fx, fy, ofb200.stream_ptr())
-        ofb200.check(rc, "ofb_scale_flow_f32")
+        rc = ofb200.load().ofb_scale_flow(ofb200.ptr(flow_d), ofb200.ptr(out), dt, b, hw, fx, fy, ofb200.stream_ptr())
+        ofb200.check(rc, "ofb_scale_flow")
         return out
 
     def backward(saved, grad_out: Tensor, needs):
