@@ -435,13 +435,19 @@ def run_ours(args):
         "peak_source": PEAKS["source"] + " (MEASURED_PEAKS.json hbm_gbs)" if PEAKS["source"] == "measured" else "fallback",
         "tensor": {"achieved": k2["tflops"], "peak": PEAKS["bf16_tflops_sustained"], "unit": "TFLOP/s",
                    "frac": k2["tensor_frac_sustained"]},
-        "note": "K=256 makes the builder write-bound: 2*N^2*C flops need 0.39 ms/pair of tensor time, the bf16 "
-                "pyramid write 0.44 ms/pair of HBM time; measured limit is the SM store path (DESIGN.md section 4)",
+        "note": "K=256 makes the builder write-bound on paper: 2*N^2*C flops need 0.39 ms/pair of tensor time, the bf16 "
+                "pyramid write 0.44 ms/pair of HBM time; measured limit in steady state is the 1 kW power cap "
+                "(992 W, 1.42 GHz when run back to back: profiles/r02_k2_power1.jsonl, DESIGN.md section 4)",
     }
+    # dram__bytes_read + dram__bytes_write of both K2 launches at this shape come from ONE `ncu --set full` capture
+    # committed under profiles/ (a profiler cannot run inside a timed region): a static figure, labelled as such
     traffic_file = os.path.join(ROOT, "profiles", "k2_traffic.json")
     if os.path.exists(traffic_file):
         try:
-            roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch_at_bench_shape")
+            tj = json.load(open(traffic_file))
+            roofline["traffic"] = tj.get("dram_bytes_per_launch_at_bench_shape")
+            roofline["traffic_source"] = "static: " + tj.get("source", "profiles/k2_traffic.json") + " -- not measured in this run"
+            roofline["algorithmic_bytes"] = tj.get("algorithmic_bytes")
         except Exception:
             pass
 
