@@ -404,6 +404,13 @@ def run_ours(args):
     e2e_fp32["input_dtypes"] = "all fp32 (round-1 configuration)"
     epe_e2e = e2e.pop("epe")
     e2e_fp32.pop("epe")
+    # informational: every tensor a `precision: 16` network produces in half precision travels that way -- the two
+    # feature maps (bf16) AND the 576-channel upsampling mask (fp16: the mask head's autocast output; 46 % of a pair's
+    # payload), read directly by ofb_convex_upsample.  Not the headline: the mask's rounding changes the upsampled flow
+    # at the 1e-3 level, so this is a different input, reported separately.
+    e2e_half = time_e2e(dict(half, up_mask=torch.float16))
+    e2e_half["input_dtypes"] = "fmap1, fmap2: bf16; up_mask: fp16; coords, flow_lo, frame, target, valid: fp32"
+    e2e_half.pop("epe")
     if rank == 0:
         sampler.stop()
 
@@ -464,6 +471,7 @@ def run_ours(args):
                    "host_affinity": affinity, "device_placement": placement},
         "e2e": dict(e2e, api="ofb200.runner.HostStagedRunner.run(pinned PairArena: one DMA per pair) -> CorrBlock / warp / upsample_flow / AverageEndPointError -> libofb200 C ABI"),
         "e2e_fp32_inputs": e2e_fp32,
+        "e2e_half_precision_producers": e2e_half,
         "gpu_launches": int(launches),
         "clocks": sampler.summary(t_wall0, t_wall1),
         "roofline": roofline,

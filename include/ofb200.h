@@ -44,7 +44,7 @@ extern "C" {
 
 #define OFB_DTYPE_F32 0
 #define OFB_DTYPE_BF16 1
-#define OFB_DTYPE_F16 2 /* input feature maps of ofb_corr_prep_from, ofb_scale_flow */
+#define OFB_DTYPE_F16 2 /* input feature maps of ofb_corr_prep_from, mask of ofb_convex_upsample, ofb_scale_flow */
 #define OFB_DTYPE_F64 3 /* ofb_scale_flow only */
 
 #define OFB_MAX_LEVELS 4
@@ -117,6 +117,10 @@ int ofb_resize_bilinear_backward_f32(const float* d_out, float* d_in, int N, int
  * (methods/raft/model/raft.py:73-85): flow (N,2,h,w), mask (N,576,h,w) -> out (N,2,8h,8w).
  * ------------------------------------------------------------------------------------- */
 int ofb_convex_upsample_f32(const float* flow, const float* mask, float* out, int N, int h, int w, void* stream);
+/* The same kernel reading the 576-channel mask in its own precision (mask_dtype OFB_DTYPE_F32 / BF16 / F16): under the
+ * reference's `precision: 16` the mask head's output is half precision (the softmax of raft.py:78 autocasts to fp32, as
+ * the kernel does after the load).  The flow and the result stay fp32. */
+int ofb_convex_upsample(const float* flow, const void* mask, int mask_dtype, float* out, int N, int h, int w, void* stream);
 /* Backward of the convex upsampling (autograd through raft.py:77-85): d_out (N,2,8h,8w), 16-byte
  * aligned.  d_mask_or_null (N,576,h,w) is overwritten; d_flow_or_null (N,2,h,w) is ACCUMULATED
  * into (zero it first).  Either may be NULL. */

@@ -442,6 +442,37 @@ def test_upsample_flow_vs_oracle_kitti_shape():
     assert maxabs(out, ref) <= tol(ref)
 
 
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_upsample_flow_half_precision_mask(dt):
+    """`precision: 16` callers hand the mask head's half-precision output to upsample_flow (reference raft.py:73-85; its
+    softmax autocasts to fp32).  Same result as the fp32 kernel on the same (rounded) logits, <= 1e-5 against the oracle
+    on them; differentiable with respect to the flow and -- through an fp32 cast -- the mask."""
+    from model.raft import upsample_flow
+
+    r = rng(95)
+    n, h, w = 2, 19, 37
+    flow = (2 * r.standard_normal((n, 2, h, w))).astype(np.float32)
+    mask_h = T((2 * r.standard_normal((n, 576, h, w))).astype(np.float32)).to(dt)
+    mask_f = mask_h.float()
+    got = upsample_flow(T(flow), mask_h)
+    assert got.dtype == torch.float32 and torch.equal(got, upsample_flow(T(flow), mask_f))
+    ref = oracle.upsample_flow(flow, N(mask_f))
+    assert maxabs(N(got), ref) <= tol(ref)
+    # gradients: flow only (half mask stays half), and flow + mask (mask cast to fp32 inside)
+    f1 = T(flow).requires_grad_(True)
+    wgt = torch.randn((n, 2, 8 * h, 8 * w), device="cuda")
+    (upsample_flow(f1, mask_h) * wgt).sum().backward()
+    f2, m2 = T(flow).requires_grad_(True), mask_f.clone().requires_grad_(True)
+    (upsample_flow(f2, m2) * wgt).sum().backward()
+    close = lambda a, b: float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())   # d flow is summed with atomics
+    assert close(f1.grad, f2.grad)
+    m3 = mask_h.clone().requires_grad_(True)
+    f3 = T(flow).requires_grad_(True)
+    (upsample_flow(f3, m3) * wgt).sum().backward()
+    assert m3.grad.dtype == dt and close(f3.grad, f2.grad)
+    assert float((m3.grad.float() - m2.grad).abs().max()) <= 1e-2 * float(m2.grad.abs().max())
+
+
 def test_upsample_flow_properties_full_size():
     """C4 16x(2+576)x47x156: a constant flow stays constant (softmax weights sum to 1) away from the
     zero-padded border; a one-hot mask (logit +50 on the centre tap) gives nearest upsampling * 8."""
@@ -1189,6 +1220,31 @@ def test_corr_pyramid_tcgen05_vs_fp32(cta_group, shape):
             assert maxabs(a, o) <= 2e-4
     for lvl, (rel, mx) in enumerate(_pyr_errors(blk.corr_pyramid, refs)):
         assert rel <= 4e-3 and mx <= 4e-2, (lvl, rel, mx)
+
+
+@pytest.mark.parametrize("shape", [(2, 256, 47, 156), (1, 256, 40, 72), (3, 64, 9, 35)])
+def test_corr_pyramid_store_and_launch_modes_agree(shape, monkeypatch):
+    """The measured K2 alternatives stay correct: every epilogue store mode (direct 32-byte register stores, TMA bulk
+    stores, software-pipelined 32-column pieces) under every launch mode (one CTA per tile, cta_group::2 pair, multicast
+    clusters) writes the same bits inside the images of all four levels."""
+    from model.corr import CorrBlock
+
+    gen = torch.Generator(device="cuda").manual_seed(91)
+    f1 = torch.randn(shape, device="cuda", generator=gen)
+    f2 = torch.randn(shape, device="cuda", generator=gen)
+    levels = 4 if min(shape[2:]) >= 8 else 3
+    ref = None
+    for epi in ("direct", "bulk", "pipe"):
+        monkeypatch.setenv("OFB_K2_EPI", epi)
+        for cg in (1, 2, 3):
+            blk = CorrBlock(f1, f2, num_levels=levels, cta_group=cg)
+            torch.cuda.synchronize()
+            got = [p.clone() for p in blk.corr_pyramid]
+            if ref is None:
+                ref = got
+            else:
+                for lvl, (a, b) in enumerate(zip(ref, got)):
+                    assert torch.equal(a, b), (epi, cg, lvl)
 
 
 def test_corr_block_is_immune_to_poisoned_allocator_memory():

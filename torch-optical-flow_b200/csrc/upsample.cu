@@ -17,8 +17,19 @@ namespace {
 constexpr int PX = 32;   // coarse pixels per CTA
 constexpr int NT = PX * 8;
 
+// mask logit -> fp32: the mask head's output is fp32, or half precision under the reference's `precision: 16`
+// (autocast convolution; softmax itself autocasts to fp32, raft.py:78)
+__device__ __forceinline__ float ld_logit(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ld_logit(const __nv_bfloat16* p) {
+    return __uint_as_float((unsigned)__ldg(reinterpret_cast<const unsigned short*>(p)) << 16);
+}
+__device__ __forceinline__ float ld_logit(const __half* p) {
+    return __half2float(__ushort_as_half(__ldg(reinterpret_cast<const unsigned short*>(p))));
+}
+
+template <typename TM>
 __global__ void __launch_bounds__(NT) convex_upsample_kernel(const float* __restrict__ flow,
-                                                             const float* __restrict__ mask,
+                                                             const TM* __restrict__ mask,
                                                              float* __restrict__ out, int N, int h, int w) {
     const int hw = h * w;
     const int lane_p = threadIdx.x % PX;
@@ -42,7 +53,7 @@ __global__ void __launch_bounds__(NT) convex_upsample_kernel(const float* __rest
             nby[ky * 3 + kx] = in ? 8.0f * __ldg(fy + yy * w + xx) : 0.0f;
         }
 
-    const float* mp = mask + (size_t)n * 576 * hw + (size_t)(i * 8) * hw + p;
+    const TM* mp = mask + (size_t)n * 576 * hw + (size_t)(i * 8) * hw + p;
     float ox[8], oy[8];
     // JG sub-columns at a time: 9*JG independent 128-byte-coalesced loads are in flight per warp before
     // the first softmax starts (the kernel is a pure stream of the 576-channel mask: latency, not math)
@@ -53,7 +64,7 @@ __global__ void __launch_bounds__(NT) convex_upsample_kernel(const float* __rest
 #pragma unroll
         for (int jj = 0; jj < JG; ++jj)
 #pragma unroll
-            for (int k = 0; k < 9; ++k) m[jj][k] = __ldg(mp + (size_t)(k * 64 + jg + jj) * hw);
+            for (int k = 0; k < 9; ++k) m[jj][k] = ld_logit(mp + (size_t)(k * 64 + jg + jj) * hw);
 #pragma unroll
         for (int jj = 0; jj < JG; ++jj) {
             float mx = m[jj][0];
@@ -173,16 +184,29 @@ __global__ void __launch_bounds__(NT) convex_upsample_bwd_kernel(const float* __
 
 }  // namespace
 
-OFB_API int ofb_convex_upsample_f32(const float* flow, const float* mask, float* out, int N, int h, int w, void* stream) {
+OFB_API int ofb_convex_upsample(const float* flow, const void* mask, int mask_dtype, float* out, int N, int h, int w,
+                                void* stream) {
     if (N == 0 || h == 0 || w == 0) return OFB_OK;   // nothing to do: empty tensors have no storage, their pointers may be null
     if (!flow || !mask || !out || N < 0 || h < 0 || w < 0) return OFB_EINVAL;
+    if (mask_dtype != OFB_DTYPE_F32 && mask_dtype != OFB_DTYPE_BF16 && mask_dtype != OFB_DTYPE_F16) return OFB_EINVAL;
     if ((size_t)N * h * w == 0) return OFB_OK;
     if (N > 65535) return OFB_EUNSUPPORTED;
     if (reinterpret_cast<uintptr_t>(out) & 15) return OFB_EALIGN;
+    if (reinterpret_cast<uintptr_t>(mask) & (mask_dtype == OFB_DTYPE_F32 ? 3 : 1)) return OFB_EALIGN;
     dim3 grid((h * w + PX - 1) / PX, N);
-    convex_upsample_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(flow, mask, out, N, h, w);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mask_dtype == OFB_DTYPE_F32)
+        convex_upsample_kernel<float><<<grid, NT, 0, st>>>(flow, reinterpret_cast<const float*>(mask), out, N, h, w);
+    else if (mask_dtype == OFB_DTYPE_BF16)
+        convex_upsample_kernel<__nv_bfloat16><<<grid, NT, 0, st>>>(flow, reinterpret_cast<const __nv_bfloat16*>(mask), out, N, h, w);
+    else
+        convex_upsample_kernel<__half><<<grid, NT, 0, st>>>(flow, reinterpret_cast<const __half*>(mask), out, N, h, w);
     OFB_LAUNCH_CHECK();
     return OFB_OK;
+}
+
+OFB_API int ofb_convex_upsample_f32(const float* flow, const float* mask, float* out, int N, int h, int w, void* stream) {
+    return ofb_convex_upsample(flow, mask, OFB_DTYPE_F32, out, N, h, w, stream);
 }
 
 OFB_API int ofb_convex_upsample_backward_f32(const float* flow, const float* mask, const float* d_out,
