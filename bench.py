@@ -301,7 +301,9 @@ def run_ours(args):
     dev_index = local
     if world > 1:
         # gloo for the CPU-side coordination of the placement probe, NCCL for everything on the device
-        dist.init_process_group("cpu:gloo,cuda:nccl")
+        import datetime
+
+        dist.init_process_group("cpu:gloo,cuda:nccl", timeout=datetime.timedelta(seconds=300))
         if not args.no_placement:
             from ofb200.runner import choose_device_set
 
