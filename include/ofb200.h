@@ -299,6 +299,21 @@ int ofb_cast_bf16(const float* src, void* dst_or_null, void* dst_t_or_null, int 
 int ofb_bilinear_sampler_f32(const float* img, const float* coords, float* out, float* mask_or_null,
                              int N, int C, int H, int W, int Ho, int Wo, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * The two passes around the backward GEMMs of CorrBlock (torch-optical-flow_b200/csrc/pool_ops.cu).
+ * ofb_pool_cast_bf16: fmap (B,C,h,w) in in_dtype -> (B, C, pitch_k) bf16, element k < (h/pool)*(w/pool) = mean of the
+ *   complete pool x pool block k (what the avg_pool2d chain of corr.py:52-54 makes of fmap2), the padding up to
+ *   pitch_k zero: the K-long B operand of ofb_gemm_nt_bf16.
+ * ofb_pool_adjoint_f32: d_levels[l] (B, (h>>l)*(w>>l), C) fp32 -> d_fmap (B,C,h,w) fp32 (overwritten):
+ *   d_fmap[b,c,y,x] = sum_l d_levels[l][b, (y>>l)*(w>>l) + (x>>l), c] / 4^l over the levels whose floor-cropped image
+ *   contains the pixel -- the adjoint of that pooling chain, fused with the (B,N,C) -> (B,C,h,w) transpose
+ *   (levels = 1: the transpose alone).
+ * ------------------------------------------------------------------------------------- */
+int ofb_pool_cast_bf16(const void* fmap_nchw, int in_dtype, void* out_bck_bf16, int B, int C, int h, int w, int pool,
+                       int pitch_k, void* stream);
+int ofb_pool_adjoint_f32(const float* const* d_levels_bnc_host, float* d_fmap_nchw, int B, int C, int h, int w, int levels,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -579,6 +579,55 @@ def test_gemm_nt_bf16_and_cast(batch, m, n, k):
     assert float((got3 - ref2).abs().max()) <= 2e-3 * float(ref2.abs().max()) + 1e-4
 
 
+@pytest.mark.parametrize("shape", [(2, 64, 47, 156), (1, 32, 9, 13), (3, 40, 17, 30)])
+def test_pool_cast_and_pool_adjoint_kernels(shape):
+    """The two passes around CorrBlock's backward GEMMs against the ATen ops they replace: the pooled K-padded bf16
+    operand = bf16(avg_pool2d chain of corr.py:52-54), and the pooling adjoint = autograd through that chain (with the
+    (B, N_l, C) -> (B, C, h, w) layout change fused)."""
+    import ctypes
+
+    import ofb200
+
+    b, c, h, w = shape
+    gen = torch.Generator(device="cuda").manual_seed(97)
+    f = torch.randn(shape, device="cuda", generator=gen)
+    lib, st = ofb200.load(), ofb200.stream_ptr()
+    levels = [f]
+    for _ in range(3):
+        if min(levels[-1].shape[-2:]) < 2:
+            break
+        levels.append(torch.nn.functional.avg_pool2d(levels[-1], 2, stride=2))
+    for lvl, ref in enumerate(levels):
+        nl = ref.shape[-2] * ref.shape[-1]
+        pk = (nl + 7) // 8 * 8 + 8
+        for src in (f, f.bfloat16(), f.half()):
+            out = torch.full((b, c, pk), 7.0, dtype=torch.bfloat16, device="cuda")
+            ofb200.check(lib.ofb_pool_cast_bf16(ofb200.ptr(src), {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}[src.dtype],
+                                                ofb200.ptr(out), b, c, h, w, 1 << lvl, pk, st), "ofb_pool_cast_bf16")
+            want = src.float()
+            for _ in range(lvl):
+                want = torch.nn.functional.avg_pool2d(want, 2, stride=2)
+            assert float(out[:, :, nl:].abs().max()) == 0.0                           # padding is written, as zeros
+            got = out[:, :, :nl].float().view(b, c, *ref.shape[-2:])
+            assert float((got - want).abs().max()) <= 2 ** -8 * float(want.abs().max()) + 1e-6   # one bf16 rounding
+    # adjoint
+    leaf = f.clone().requires_grad_(True)
+    chain, cur = [leaf], leaf
+    for _ in range(len(levels) - 1):
+        cur = torch.nn.functional.avg_pool2d(cur, 2, stride=2)
+        chain.append(cur)
+    grads = [torch.randn_like(t) for t in chain]
+    want = torch.autograd.grad(chain, leaf, grads)[0]
+    d_bnc = [g.reshape(b, c, -1).transpose(1, 2).contiguous() for g in grads]          # (B, N_l, C), the GEMMs' layout
+    ptrs = (ctypes.c_void_p * ofb200.MAX_LEVELS)(*[t.data_ptr() for t in d_bnc])
+    got = torch.empty_like(f)
+    ofb200.check(lib.ofb_pool_adjoint_f32(ptrs, ofb200.ptr(got), b, c, h, w, len(d_bnc), st), "ofb_pool_adjoint_f32")
+    assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max())
+    one = (ctypes.c_void_p * ofb200.MAX_LEVELS)(d_bnc[0].data_ptr())
+    ofb200.check(lib.ofb_pool_adjoint_f32(one, ofb200.ptr(got), b, c, h, w, 1, st), "ofb_pool_adjoint_f32")
+    assert torch.equal(got, grads[0])                                                  # levels = 1: the transpose alone
+
+
 def test_corr_block_backward(golden):
     """CorrBlock gradients with respect to the feature maps: the reference's autograd result (two lookups into one
     pyramid, tests/golden/corr_grad.npz), then other shapes / radii / level counts against autograd through

@@ -73,6 +73,8 @@ SIGNATURES = {
     "ofb_corr_pyramid_simt_f32": (_i, [_vp, _vp, ctypes.POINTER(Pyramid), _i, _i, _i, _i, _f, _vp]),
     "ofb_gemm_nt_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i] + [ctypes.c_longlong] * 6 + [_f, _i, _vp]),
     "ofb_cast_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, ctypes.c_longlong, ctypes.c_longlong, _vp]),
+    "ofb_pool_cast_bf16": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "ofb_pool_adjoint_f32": (_i, [ctypes.POINTER(_vp), _vp, _i, _i, _i, _i, _i, _vp]),
     "ofb_corr_lookup_backward_f32": (_i, [ctypes.POINTER(Pyramid), _vp, _vp, _i, _i, _i, _i, _vp]),
     "ofb_corr_lookup": (_i, [ctypes.POINTER(Pyramid), _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "ofb_corr_lookup_ondemand": (_i, [_vp, ctypes.POINTER(_vp), _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

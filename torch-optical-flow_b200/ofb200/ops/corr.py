@@ -110,7 +110,9 @@ class _PyramidHandle(torch.autograd.Function):
     pyramid is complete, and turns it into feature-map gradients:
         pyr_l = fmap1^T . pool_l(fmap2) / sqrt(C)        (pooling is linear, reference corr.py:45-54)
         d fmap1 = sum_l pool_l(fmap2) . dP_l^T / sqrt(C);  d pool_l(fmap2) = fmap1 . dP_l / sqrt(C)
-    (library GEMMs over the dense fp32 gradient levels), and the pooling adjoint through autograd."""
+    With a bf16 pyramid (default) all of it runs on this library's kernels: pooled bf16 operands, the long-K tcgen05
+    GEMMs, and a fused pooling-adjoint + layout pass; with an fp32 pyramid (the parity configuration) the GEMMs are fp32
+    library GEMMs and the pooling adjoint goes through autograd."""
 
     @staticmethod
     def forward(ctx, state, fmap1, fmap2):
@@ -127,13 +129,6 @@ class _PyramidHandle(torch.autograd.Function):
         task = torch._C._current_graph_task_id() if hasattr(torch._C, "_current_graph_task_id") else None
         if blk.dpyr is not None and blk.task == task:
             scale = 1.0 / math.sqrt(float(c))
-            f1 = fmap1.float().reshape(b, c, h * w)
-            with torch.enable_grad():
-                leaf = fmap2.float().detach().requires_grad_(True)
-                levels, cur = [leaf], leaf
-                for _ in range(blk.num_levels - 1):
-                    cur = torch.nn.functional.avg_pool2d(cur, 2, stride=2)
-                    levels.append(cur)
             # The two GEMMs per level.  "tcgen05" (default with a bf16 pyramid): bf16 operands, fp32 accumulation, this
             # library's long-K tensor-core kernel fed by one cast / transpose pass over the fp32 gradient level --
             # the precision of a `precision: 16` run of the reference.  "fp32" (default with an fp32 pyramid; matches
@@ -144,31 +139,53 @@ class _PyramidHandle(torch.autograd.Function):
                 raise NotImplementedError("CorrBlock backward: the tcgen05 GEMM needs C to be a multiple of 32, at most 256")
             d_levels = []
             if mode == "tcgen05":
+                # everything on this library's kernels: pooled bf16 operands (ofb_pool_cast_bf16), one cast / transpose
+                # pass per gradient level (ofb_cast_bf16), the two long-K tcgen05 GEMMs (ofb_gemm_nt_bf16), and one
+                # pooling-adjoint + layout pass per feature map (ofb_pool_adjoint_f32)
                 lib, st = ofb200.load(), ofb200.stream_ptr()
+                dev = fmap1.device
                 n = h * w
                 pn = (n + 7) // 8 * 8
-                d1t = torch.zeros((b, n, c), dtype=torch.float32, device=f1.device)            # d fmap1^T, summed over levels
-                f1_16 = torch.zeros((b, c, pn), dtype=torch.bfloat16, device=f1.device)
-                f1_16[:, :, :n] = f1
-                for lvl, f2l in enumerate(levels):
-                    hl, wl = f2l.shape[-2:]
+                f1c, f2c = fmap1.contiguous(), fmap2.contiguous()
+                d1t = torch.zeros((b, n, c), dtype=torch.float32, device=dev)                  # d fmap1^T, summed over levels
+                f1_16 = torch.empty((b, c, pn), dtype=torch.bfloat16, device=dev)
+                ofb200.check(lib.ofb_pool_cast_bf16(ofb200.ptr(f1c), _IN_DTYPES[f1c.dtype], ofb200.ptr(f1_16), b, c, h, w, 1, pn, st),
+                             "ofb_pool_cast_bf16")
+                d2_levels = []
+                for lvl in range(blk.num_levels):
+                    hl, wl = h >> lvl, w >> lvl
                     nl = hl * wl
                     pk = (nl + 7) // 8 * 8
-                    a16 = torch.empty((b, n, pk), dtype=torch.bfloat16, device=f1.device)      # bf16(dP_l)
-                    a16_t = torch.empty((b, nl, pn), dtype=torch.bfloat16, device=f1.device)   # bf16(dP_l)^T
+                    a16 = torch.empty((b, n, pk), dtype=torch.bfloat16, device=dev)            # bf16(dP_l)
+                    a16_t = torch.empty((b, nl, pn), dtype=torch.bfloat16, device=dev)         # bf16(dP_l)^T
                     ofb200.check(lib.ofb_cast_bf16(ofb200.ptr(blk.dpyr[lvl]), ofb200.ptr(a16), ofb200.ptr(a16_t), b, n, nl,
                                                    pk, pn, st), "ofb_cast_bf16")
                     blk.dpyr[lvl] = None                                                        # free level by level
-                    f2_16 = torch.zeros((b, c, pk), dtype=torch.bfloat16, device=f1.device)
-                    f2_16[:, :, :nl] = f2l.detach().reshape(b, c, nl)
+                    f2_16 = torch.empty((b, c, pk), dtype=torch.bfloat16, device=dev)          # bf16(avgpool_l(fmap2)), K-padded
+                    ofb200.check(lib.ofb_pool_cast_bf16(ofb200.ptr(f2c), _IN_DTYPES[f2c.dtype], ofb200.ptr(f2_16), b, c, h, w,
+                                                        1 << lvl, pk, st), "ofb_pool_cast_bf16")
                     ofb200.check(lib.ofb_gemm_nt_bf16(ofb200.ptr(a16), ofb200.ptr(f2_16), ofb200.ptr(d1t), b, n, c, nl, pk, pk, c,
                                                       n * pk, c * pk, n * c, scale, 1, st), "ofb_gemm_nt_bf16")
-                    d2t = torch.empty((b, nl, c), dtype=torch.float32, device=f1.device)
+                    d2t = torch.empty((b, nl, c), dtype=torch.float32, device=dev)
                     ofb200.check(lib.ofb_gemm_nt_bf16(ofb200.ptr(a16_t), ofb200.ptr(f1_16), ofb200.ptr(d2t), b, nl, c, n, pn, pn, c,
                                                       nl * pn, c * pn, nl * c, scale, 0, st), "ofb_gemm_nt_bf16")
-                    d_levels.append(d2t.transpose(1, 2).reshape(b, c, hl, wl))
-                d1 = d1t.transpose(1, 2).contiguous()
+                    d2_levels.append(d2t)
+                d1 = torch.empty((b, c, h, w), dtype=torch.float32, device=dev)
+                d2 = torch.empty((b, c, h, w), dtype=torch.float32, device=dev)
+                one = (ctypes.c_void_p * ofb200.MAX_LEVELS)(d1t.data_ptr())
+                ofb200.check(lib.ofb_pool_adjoint_f32(one, ofb200.ptr(d1), b, c, h, w, 1, st), "ofb_pool_adjoint_f32")
+                ptrs = (ctypes.c_void_p * ofb200.MAX_LEVELS)(*[t.data_ptr() for t in d2_levels])
+                ofb200.check(lib.ofb_pool_adjoint_f32(ptrs, ofb200.ptr(d2), b, c, h, w, blk.num_levels, st), "ofb_pool_adjoint_f32")
+                d1 = d1.to(fmap1.dtype)
+                d2 = d2.to(fmap2.dtype)
             else:
+                f1 = fmap1.float().reshape(b, c, h * w)
+                with torch.enable_grad():
+                    leaf = fmap2.float().detach().requires_grad_(True)
+                    levels, cur = [leaf], leaf
+                    for _ in range(blk.num_levels - 1):
+                        cur = torch.nn.functional.avg_pool2d(cur, 2, stride=2)
+                        levels.append(cur)
                 gemm_dt = torch.bfloat16 if mode == "bf16" else torch.float32
                 f1g = f1.to(gemm_dt)
                 d1 = torch.zeros_like(f1)
@@ -179,9 +196,9 @@ class _PyramidHandle(torch.autograd.Function):
                     d1.add_(torch.bmm(f2g, dp.transpose(1, 2)).float(), alpha=scale)
                     d_levels.append((torch.bmm(f1g, dp).float() * scale).view(b, c, hl, wl))
                     blk.dpyr[lvl] = None                                                # free level by level
-            d2 = torch.autograd.grad(levels, leaf, d_levels)[0]
-            d1 = d1.view(b, c, h, w).to(fmap1.dtype)
-            d2 = d2.to(fmap2.dtype)
+                d2 = torch.autograd.grad(levels, leaf, d_levels)[0]
+                d1 = d1.view(b, c, h, w).to(fmap1.dtype)
+                d2 = d2.to(fmap2.dtype)
         blk.release()                                                            # free the gradient pyramid
         need1, need2 = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         return None, (d1 if need1 else None), (d2 if need2 else None)
